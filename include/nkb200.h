@@ -1,0 +1,200 @@
+/*
+ * nkb200 — C ABI of the B200-native VMC inner loop (Metropolis sweep + local energy for RBM).
+ *
+ * This header is the drop-in boundary.  The reference (NetKet) has no FFI of its own: its
+ * extension points are Python-level.  Each entry point below states the
+ * reference function it replaces (paths relative to /root/reference).  INTEGRATION.md shows
+ * the reference-side binding (ctypes / jax.ffi) a maintainer would add.
+ *
+ * Conventions
+ *   - plain C, no torch / jax types; every pointer is a DEVICE pointer unless the name ends
+ *     in `_host`; the caller owns every buffer; nothing is allocated or freed inside except
+ *     by the nk_ctx_* host-buffer API at the bottom of this file;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never
+ *     synchronises the device, and is safe to call concurrently from different host threads
+ *     on different devices (no mutable globals; the error string is thread-local);
+ *   - returns 0 on success, a negative NK_E* code otherwise; nk_last_error() gives the text;
+ *   - sigma is int8 with values +1 / -1 (netket/hilbert/spin.py:165-171: local index 0 <-> +1,
+ *     1 <-> -1); parameters follow Flax's layout: W (N, M) row-major "in x out", b (M), a (N)
+ *     (netket/models/rbm.py:59-79);
+ *   - dtype codes: NK_F32 / NK_F64 (parameter and log-amplitude precision).
+ */
+#ifndef NKB200_H
+#define NKB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NK_VERSION 100
+
+#define NK_F32 0
+#define NK_F64 1
+
+#define NK_OK 0
+#define NK_EINVAL (-1)   /* bad argument (shape, dtype, null pointer) */
+#define NK_ECUDA (-2)    /* CUDA runtime error, text in nk_last_error() */
+#define NK_EUNSUPPORTED (-3)
+
+#define NK_RULE_LOCAL 0    /* netket/sampler/rules/local.py:23-52 */
+#define NK_RULE_EXCHANGE 1 /* netket/sampler/rules/exchange.py:25-187, probabilities=None */
+
+/* kernel-path selection for the sweep / E_loc kernels (NK_PATH_AUTO picks the fastest valid one) */
+#define NK_PATH_AUTO 0
+#define NK_PATH_GENERIC 1 /* theta-form, lncosh differences; any shape, any |W| */
+#define NK_PATH_FAST 2    /* product form on tanh tables resident in shared memory */
+
+typedef struct nk_rbm_t {
+  const void *W; /* [N, M] */
+  const void *b; /* [M] or NULL   (use_hidden_bias=False) */
+  const void *a; /* [N] or NULL   (use_visible_bias=False) */
+  int32_t N;     /* visible units = sites */
+  int32_t M;     /* hidden units = alpha * N */
+  int32_t dtype; /* NK_F32 | NK_F64 */
+  int32_t reserved;
+} nk_rbm_t;
+
+/* Transverse-field Ising  H = -h sum_i sx_i + J sum_<ij> sz_i sz_j  (netket/operator/_ising/jax.py:35-175) */
+typedef struct nk_ising_t {
+  const int32_t *edges; /* [E, 2] */
+  int32_t n_edges;
+  int32_t reserved;
+  double h; /* h == 0 => StaticZero: K = 1 (jax.py:60-61,127-131,156-157) */
+  double J;
+} nk_ising_t;
+
+/* One group of LocalOperator terms acting on the same number of sites (1 or 2), i.e. the packed
+ * lookup tables of netket/operator/_local_operator/compile_helpers.py:29-218. */
+typedef struct nk_localop_group_t {
+  int32_t n_ops;
+  int32_t n_sites; /* 1 or 2 */
+  int32_t ncmax;   /* padded number of off-diagonal entries per row */
+  int32_t reserved;
+  const int32_t *acting_on; /* [n_ops, n_sites] */
+  const double *diag_mels;  /* [n_ops, 2^n_sites] */
+  const int32_t *n_conns;   /* [n_ops, 2^n_sites] */
+  const double *mels;       /* [n_ops, 2^n_sites, ncmax]  (padding may be NaN, never read) */
+  const int8_t *x_prime;    /* [n_ops, 2^n_sites, ncmax, n_sites] local indices 0/1 */
+} nk_localop_group_t;
+
+typedef struct nk_localop_t {
+  nk_localop_group_t groups[2];
+  int32_t n_groups;
+  int32_t nonzero_diagonal;
+  int32_t max_conn_size; /* K */
+  int32_t reserved;
+  double constant;
+  double mel_cutoff; /* 1e-10 (netket/operator/_local_operator/base.py:90) */
+} nk_localop_t;
+
+/* Markov-chain state = MetropolisSamplerState (netket/sampler/metropolis.py:42-137). */
+typedef struct nk_chains_t {
+  int8_t *sigma;         /* [B, N] in/out */
+  void *log_prob;        /* [B] dtype; out: machine_pow * logpsi(sigma) after the call */
+  int64_t *n_accepted;   /* [B] in/out, incremented (n_accepted_proc) */
+  void *workspace;       /* nk_sweep_workspace_bytes() bytes of scratch (theta); contents are derived state */
+  int64_t B;             /* chains on this device */
+  uint64_t seed;         /* Philox key */
+  uint64_t t;            /* Metropolis steps already performed per chain (Philox counter) */
+  uint64_t chain_offset; /* global index of chain 0 of this device (multi-GPU sharding) */
+} nk_chains_t;
+
+typedef struct nk_sweep_t {
+  int32_t rule;         /* NK_RULE_* */
+  int32_t chain_length; /* recorded sweeps */
+  int32_t n_discard;    /* burn-in sweeps run before, not recorded (mc_state/state.py:559-568) */
+  int32_t sweep_size;   /* MH steps per sweep, default N (metropolis.py:283-284) */
+  double machine_pow;   /* default 2 (sampler/base.py:139-150) */
+  int8_t *samples_out;  /* [B, chain_length, N] or NULL */
+  void *logp_out;       /* [B, chain_length] dtype or NULL (return_log_probabilities) */
+  /* optional explicit proposal stream (fixed-proposal-stream mode), indexed [step, chain] with
+   * step in [0, (n_discard+chain_length)*sweep_size); NULL => in-kernel Philox4x32-10 */
+  const uint32_t *stream_w0;
+  const void *stream_u; /* dtype */
+  /* ExchangeRule */
+  const int32_t *clusters; /* [C, 2] */
+  int32_t n_clusters;
+  int32_t path; /* NK_PATH_* */
+  /* optional fused local energy of every recorded sample (sigma' never materialised) */
+  const nk_ising_t *ising;     /* or NULL */
+  const nk_localop_t *localop; /* or NULL */
+  void *eloc_out;              /* [B, chain_length] */
+  int32_t eloc_dtype;          /* NK_F32 | NK_F64 = promote(operator dtype, rbm dtype) */
+  int32_t reserved;
+} nk_sweep_t;
+
+const char *nk_last_error(void);
+int nk_version(void);
+
+/* RBM.apply: logpsi[B] = sum_j lncosh(sum_i sigma_i W_ij + b_j) + sum_i a_i sigma_i.
+ * Replaces netket/models/rbm.py:57-81 + netket/nn/activation.py:78-84 (seam S5).
+ * theta_out (optional, [B, M]) receives the hidden pre-activations. */
+int nk_rbm_logpsi(void *stream, const nk_rbm_t *rbm, const int8_t *sigma, int64_t B, void *logpsi_out, void *theta_out);
+
+/* theta[B, M] = sigma W + b as a tensor-core GEMM (tcgen05 for fp32 via exact 3-way bf16 split, DMMA for
+ * fp64).  Replaces the nn.Dense half of netket/models/rbm.py:59-67 at `_reset`
+ * (netket/sampler/metropolis.py:399-403).  workspace: nk_theta_gemm_workspace_bytes(). */
+int64_t nk_theta_gemm_workspace_bytes(const nk_rbm_t *rbm, int64_t B);
+int nk_theta_gemm(void *stream, const nk_rbm_t *rbm, const int8_t *sigma, int64_t B, void *theta_out, void *workspace);
+
+/* hilbert.random_state for Spin-1/2 (netket/hilbert/random/homogeneous.py:35-72, random/fock.py:77-97).
+ * n_down < 0: unconstrained; otherwise exactly n_down sites are -1 (total_sz constraint). */
+int nk_random_state(void *stream, int8_t *sigma, int64_t B, int32_t N, int32_t n_down, uint64_t seed, uint64_t chain_offset);
+
+/* MetropolisSampler._reset + _sample_chain (netket/sampler/metropolis.py:382-505) for LocalRule /
+ * ExchangeRule on an RBM, optionally fused with local_value_kernel_jax (netket/vqs/mc/kernels.py:62-71). */
+int64_t nk_sweep_workspace_bytes(const nk_rbm_t *rbm, int64_t B);
+int nk_sweep(void *stream, const nk_rbm_t *rbm, nk_chains_t *chains, const nk_sweep_t *args);
+
+/* IsingJax.get_conn_padded (netket/operator/_ising/jax.py:82-88,125-165).
+ * xp_out [B, K, N] int8, mels_out [B, K] (mel_dtype), K = N+1 (1 if h == 0). */
+int nk_ising_conn(void *stream, const nk_ising_t *op, const int8_t *x, int64_t B, int32_t N, int8_t *xp_out, void *mels_out,
+                  int32_t mel_dtype);
+/* IsingJax.n_conn (jax.py:71-80,168-175) */
+int nk_ising_n_conn(void *stream, const nk_ising_t *op, const int8_t *x, int64_t B, int32_t N, int32_t *nconn_out);
+
+/* LocalOperatorJax._get_conn_padded (netket/operator/_local_operator/jax.py:74-201,256-284):
+ * xp_out [B, K, N] int8, mels_out [B, K], nconn_out [B] (may be NULL). */
+int nk_localop_conn(void *stream, const nk_localop_t *op, const int8_t *x, int64_t B, int32_t N, int8_t *xp_out, void *mels_out,
+                    int32_t mel_dtype, int32_t *nconn_out);
+
+/* local_value_kernel_jax for (RBM, Ising) and (RBM, LocalOperator) without materialising sigma'
+ * (netket/vqs/mc/kernels.py:62-71; seam S4).  eloc_out [B] (eloc_dtype). */
+int nk_eloc_ising_rbm(void *stream, const nk_rbm_t *rbm, const nk_ising_t *op, const int8_t *sigma, int64_t B, void *eloc_out,
+                      int32_t eloc_dtype, int32_t path);
+int nk_eloc_localop_rbm(void *stream, const nk_rbm_t *rbm, const nk_localop_t *op, const int8_t *sigma, int64_t B, void *eloc_out,
+                        int32_t eloc_dtype);
+
+/* statistics() (netket/stats/mc_stats_old.py:52-196), split so that only scalars cross devices:
+ *   phase 0: partials_out[0] = sum(x)                                    -> all-reduce -> mean
+ *   phase 1: partials_out[0..6] = shifted second moments around `shift`  -> all-reduce
+ * then nk_stats_finalize on the host.  data [n_chains, L] (dtype).  partials_out: 8 doubles (device). */
+#define NK_STATS_NPARTIAL 8
+int nk_stats_partial(void *stream, const void *data, int32_t dtype, int64_t n_chains, int64_t L, int32_t phase, double shift,
+                     double *partials_out);
+/* host-only arithmetic: sums_host = all-reduced phase-1 partials; out_host = {mean, error_of_mean, variance, tau_corr, R_hat} */
+int nk_stats_finalize(const double *sums_host, double mean, int64_t n_chains_total, int64_t L, double *out_host);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host-buffer API: one VMC inner-loop step with HOST pointers (what bench.py's `e2e` times).
+ * The context owns the device buffers (parameters, chains, operator tables, E_loc).
+ * Mirrors   vs.parameters = ...; vs.reset(); vs.expect(H)   of
+ * netket/vqs/mc/mc_state/state.py:514-576,695-712 for (MetropolisLocal, RBM, Ising).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct nk_ctx nk_ctx;
+int nk_ctx_create(nk_ctx **out, int32_t device, int32_t N, int32_t M, int32_t dtype, int64_t n_chains, int32_t chain_length,
+                  const int32_t *edges_host, int32_t n_edges, double h, double J, uint64_t seed, uint64_t chain_offset);
+void nk_ctx_destroy(nk_ctx *ctx);
+/* upload parameters (pinned or pageable host memory), run n_discard + chain_length sweeps fused with E_loc,
+ * copy E_loc [n_chains, chain_length] (dtype) and the 5 statistics + acceptance back to host; synchronises. */
+int nk_ctx_step_host(nk_ctx *ctx, const void *W_host, const void *b_host, const void *a_host, int32_t n_discard,
+                     void *eloc_host, double *stats_host /* [6]: mean, err, var, tau, rhat, acceptance */);
+/* copy the current configurations sigma [n_chains, N] to host */
+int nk_ctx_get_sigma_host(nk_ctx *ctx, int8_t *sigma_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NKB200_H */

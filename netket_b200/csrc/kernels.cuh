@@ -1,0 +1,40 @@
+// Internal launcher declarations shared between the translation units of libnkb200.
+#pragma once
+
+#include "common.cuh"
+
+namespace nk {
+
+struct SweepKernelArgs {
+  nk_rbm_t rbm;
+  // chains
+  int8_t *sigma;
+  void *log_prob;
+  int64_t *n_accepted;
+  int64_t B;
+  uint64_t seed, t0, chain_offset;
+  // sweep
+  int32_t rule, chain_length, n_discard, sweep_size;
+  double machine_pow;
+  int8_t *samples_out;
+  void *logp_out;
+  const uint32_t *stream_w0;
+  const void *stream_u;
+  const int32_t *clusters;
+  int32_t n_clusters;
+  // fused E_loc
+  int32_t eloc_kind;  // 0 none, 1 ising, 2 localop
+  nk_ising_t ising;
+  nk_localop_t localop;
+  void *eloc_out;
+  int32_t eloc_dtype;
+  int32_t n_pad;  // per-warp sigma stride in smem
+};
+
+// sweep_generic.cu — theta-form path (any shape / dtype / rule)
+int sweep_generic(cudaStream_t stream, const SweepKernelArgs &a);
+// sweep_fast.cu — product-form path (fp32 LocalRule, tanh table resident in shared memory)
+bool sweep_fast_supported(const SweepKernelArgs &a);
+int sweep_fast(cudaStream_t stream, const SweepKernelArgs &a);
+
+}  // namespace nk

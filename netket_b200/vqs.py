@@ -1,0 +1,269 @@
+"""``nk.vqs.MCState``: sample() / samples / log_value / local_estimators / expect.
+
+Mirrors netket/vqs/mc/mc_state/state.py:123-959 for the (Metropolis sampler, RBM) pair:
+
+* ``n_samples`` is rounded up to a multiple of ``n_chains`` (``compute_chain_length``, state.py:60-79), default
+  = first multiple of ``n_chains`` >= 1000 (:306-309); ``n_discard_per_chain`` default 5 (:466-468).
+* ``sample()`` always resets the sampler first, runs ``n_discard_per_chain`` burn-in sweeps and then
+  ``chain_length`` recorded sweeps (:521-576).  ``samples`` is cached until ``reset()``; assigning ``parameters``
+  / ``variables`` calls ``reset()`` (netket/vqs/base.py:88-116).
+* ``expect(O)`` = ``local_estimators(O).to_stats()`` (mc_state/expect.py:124-128, local_estimators.py:34-82).
+  If no samples are cached the sweep kernel is launched *fused* with the local energy (theta stays on chip and
+  sigma' is never materialised); with cached samples the stand-alone E_loc kernel runs on them.  Both give the
+  same numbers (tests/test_mcstate_gpu.py).
+* ``chunk_size`` is accepted and ignored: results are chunk-invariant by the reference's own tests
+  (test/variational/test_variational.py:497-515) and the fused kernels have nothing to chunk.
+"""
+
+import ctypes as C
+import warnings
+
+import numpy as np
+import torch
+
+from . import _lib
+from .models import RBM
+from .operator import IsingJax, LocalOperatorJax
+from .stats import Stats, statistics
+from .utils import mix_seed, split_seed, world
+
+
+def compute_chain_length(n_chains, n_samples):
+    """state.py:60-79."""
+    if n_samples <= 0:
+        raise ValueError(f"Invalid number of samples: n_samples={n_samples}")
+    chain_length = int(np.ceil(n_samples / n_chains))
+    n_new = chain_length * n_chains
+    if n_new != n_samples:
+        _, ws = world()
+        warnings.warn(f"n_samples={n_samples} ({n_samples // ws} per device) does not divide n_chains={n_chains}, "
+                      f"increased to {n_new} ({n_new // ws} per device)", UserWarning, stacklevel=3)
+    return chain_length
+
+
+class LocalEstimators:
+    """netket/_src/stats/local_estimators.py:47-129 (``data`` (n_chains, chain_length), ``to_stats``)."""
+
+    def __init__(self, data):
+        self.data = data
+
+    def to_stats(self):
+        return statistics(self.data)
+
+    @property
+    def shape(self):
+        return tuple(self.data.shape)
+
+
+class MCState:
+    def __init__(self, sampler, model=None, *, n_samples=None, n_samples_per_rank=None, n_discard_per_chain=None,
+                 chunk_size=None, variables=None, seed=None, sampler_seed=None):
+        if model is None:
+            raise ValueError("MCState needs a model (netket_b200.models.RBM)")
+        if not isinstance(model, RBM):
+            raise NotImplementedError(f"{type(model).__name__}: MCState's fused kernels recognise netket_b200.models.RBM only")
+        self._model = model
+        self._sampler = sampler
+        seed = split_seed(seed)
+        self._sampler_seed = split_seed(sampler_seed) if sampler_seed is not None else mix_seed(seed, 7)
+        if variables is None:
+            variables = model.init(seed & 0xFFFFFFFF, sampler.hilbert.size)
+        self._variables = variables
+        self.sampler_state = sampler.init_state(model, variables, seed=self._sampler_seed)
+        self._samples = None
+        self._eloc_cache = {}
+        self._chain_length = None
+        _, ws = world()
+        if n_samples is not None and n_samples_per_rank is not None:
+            raise ValueError("Only one argument between `n_samples` and `n_samples_per_rank`can be specified at the same time.")
+        if n_samples_per_rank is not None:
+            n_samples = n_samples_per_rank * ws
+        if n_samples is None:
+            n_samples = sampler.n_chains * int(np.ceil(1000 / sampler.n_chains))  # state.py:306-309
+        self.n_samples = n_samples
+        self.n_discard_per_chain = n_discard_per_chain
+        self.chunk_size = chunk_size
+
+    # ------------------------------------------------------------------ properties
+    @property
+    def model(self):
+        return self._model
+
+    @property
+    def hilbert(self):
+        return self._sampler.hilbert
+
+    @property
+    def sampler(self):
+        return self._sampler
+
+    @sampler.setter
+    def sampler(self, s):
+        self._sampler = s
+        self.sampler_state = s.init_state(self._model, self._variables, seed=self._sampler_seed)
+        self.reset()
+
+    @property
+    def variables(self):
+        return self._variables
+
+    @variables.setter
+    def variables(self, v):
+        self._variables = v
+        self.reset()
+
+    @property
+    def parameters(self):
+        return self._variables["params"]
+
+    @parameters.setter
+    def parameters(self, p):
+        self._variables = {**self._variables, "params": p}
+        self.reset()
+
+    @property
+    def model_state(self):
+        return {}
+
+    @property
+    def n_parameters(self):
+        W, b, a = RBM.unpack(self._variables)
+        return W.numel() + (b.numel() if b is not None else 0) + (a.numel() if a is not None else 0)
+
+    @property
+    def n_samples(self):
+        return self._chain_length * self._sampler.n_chains
+
+    @n_samples.setter
+    def n_samples(self, n):
+        self.chain_length = compute_chain_length(self._sampler.n_chains, n)
+
+    @property
+    def n_samples_per_rank(self):
+        return self._chain_length * self._sampler.n_chains_per_rank
+
+    @property
+    def chain_length(self):
+        return self._chain_length
+
+    @chain_length.setter
+    def chain_length(self, L):
+        if L <= 0:
+            raise ValueError(f"Invalid chain length: chain_length={L}")
+        self._chain_length = int(L)
+        self.reset()
+
+    @property
+    def n_discard_per_chain(self):
+        return self._n_discard
+
+    @n_discard_per_chain.setter
+    def n_discard_per_chain(self, n):
+        if n is not None and n < 0:
+            raise ValueError(f"Invalid number of discarded samples: n_discard_per_chain={n}")
+        self._n_discard = 5 if n is None else int(n)  # state.py:466-468
+
+    @property
+    def chunk_size(self):
+        return self._chunk_size
+
+    @chunk_size.setter
+    def chunk_size(self, c):
+        if c is not None and (not isinstance(c, int) or c <= 0):
+            raise ValueError("Chunk size must be a positive integer or None.")
+        self._chunk_size = c
+
+    # ------------------------------------------------------------------ sampling
+    def reset(self):
+        """Drop the cached samples so that the next access re-samples (state.py:514-519)."""
+        self._samples = None
+        self._eloc_cache = {}
+
+    def _run(self, chain_length, n_discard, operator=None, path=_lib.NK_PATH_AUTO):
+        sa = self._sampler
+        # sampler.reset: counters zeroed (and chains re-randomised if reset_chains); log_prob is rebuilt in-kernel
+        st = self.sampler_state.replace(n_steps_proc=0, n_accepted_proc=torch.zeros_like(self.sampler_state.n_accepted_proc))
+        if sa.reset_chains:
+            st = sa.reset(self._model, self._variables, st)
+        samples, _, eloc, st = sa._launch(self._model, self._variables, st, chain_length, n_discard=n_discard,
+                                          operator=operator, path=path)
+        self.sampler_state = st
+        return samples, eloc
+
+    def sample(self, *, chain_length=None, n_samples=None, n_discard_per_chain=None):
+        """state.py:521-576."""
+        if n_samples is None and chain_length is None:
+            chain_length = self._chain_length
+        else:
+            if chain_length is None:
+                chain_length = compute_chain_length(self._sampler.n_chains, n_samples)
+            self._chain_length = chain_length
+        if n_discard_per_chain is None:
+            n_discard_per_chain = self._n_discard
+        self.reset()
+        self._samples, _ = self._run(chain_length, n_discard_per_chain)
+        return self._samples
+
+    @property
+    def samples(self):
+        if self._samples is None:
+            self.sample()
+        return self._samples
+
+    def log_value(self, sigma):
+        """state.py:594-610."""
+        return self._model.apply(self._variables, sigma)
+
+    # ------------------------------------------------------------------ estimators
+    def _check_operator(self, op):
+        if not isinstance(op, (IsingJax, LocalOperatorJax)):
+            raise NotImplementedError(
+                f"no local-estimator kernel registered for (MCState, {type(op).__name__}): supported operators are Ising, "
+                "Heisenberg / GraphOperator / LocalOperator with 1- and 2-site terms")
+        if op.hilbert != self.hilbert:
+            raise TypeError("Hilbert spaces of the state and of the operator do not match")
+
+    def _eloc_on_samples(self, op, sigma, path=_lib.NK_PATH_AUTO):
+        """Stand-alone E_loc on sigma[..., N]."""
+        rbm = RBM.c_struct(self._variables)
+        W, _, _ = RBM.unpack(self._variables)
+        dev = W.device
+        shape = tuple(sigma.shape[:-1])
+        s8 = sigma.reshape(-1, rbm.N).to(torch.int8).contiguous()
+        B = s8.shape[0]
+        out_dtype = torch.promote_types(_lib.torch_dtype(op.dtype), W.dtype)
+        out = torch.empty((B,), dtype=out_dtype, device=dev)
+        st = op._c_struct(dev)
+        with torch.cuda.device(dev):
+            if isinstance(op, IsingJax):
+                _lib.check(_lib.lib().nk_eloc_ising_rbm(_lib.stream_ptr(dev), C.byref(rbm), C.byref(st), _lib.ptr(s8), B,
+                                                        _lib.ptr(out), _lib.dtype_code(out_dtype), path))
+            else:
+                _lib.check(_lib.lib().nk_eloc_localop_rbm(_lib.stream_ptr(dev), C.byref(rbm), C.byref(st), _lib.ptr(s8), B,
+                                                          _lib.ptr(out), _lib.dtype_code(out_dtype)))
+        return out.reshape(shape)
+
+    def local_estimators(self, op, *, chunk_size=None):
+        """O_loc for every sample, shape (n_chains_per_rank, chain_length) (state.py:612-692)."""
+        self._check_operator(op)
+        key = id(op)
+        if key in self._eloc_cache:
+            return self._eloc_cache[key]
+        if self._samples is None:
+            self._samples, eloc = self._run(self._chain_length, self._n_discard, operator=op)
+        else:
+            eloc = self._eloc_on_samples(op, self._samples)
+        self._eloc_cache = {key: eloc}
+        return eloc
+
+    def expect(self, op):
+        """<O> with MC statistics (state.py:695-712)."""
+        return statistics(self.local_estimators(op))
+
+    def expect_and_grad(self, op, **kw):
+        raise NotImplementedError("expect_and_grad is the next tier (SURVEY.md §8f rank 1) and is not built yet")
+
+    def __repr__(self):
+        return (f"MCState(\n  hilbert = {self.hilbert},\n  sampler = {self._sampler},\n  n_samples = {self.n_samples},\n"
+                f"  n_discard_per_chain = {self._n_discard},\n  sampler_state = {self.sampler_state},\n"
+                f"  n_parameters = {self.n_parameters})")
