@@ -112,9 +112,13 @@ int nk_random_state(void *stream, int8_t *sigma, int64_t B, int32_t N, int32_t n
   return random_state((cudaStream_t)stream, sigma, B, N, n_down, seed, chain_offset);
 }
 
+// workspace layout of the fast path: [theta: B*M floats | pad to 256] [flags: 256 B] [scratch: B floats]
+static inline size_t ws_theta_bytes(const nk_rbm_t *rbm, int64_t B) { return (((size_t)B * rbm->M * 4) + 255) & ~(size_t)255; }
+
 int64_t nk_sweep_workspace_bytes(const nk_rbm_t *rbm, int64_t B) {
   if (check_rbm(rbm, "nk_sweep_workspace_bytes") || B < 0) return -1;
-  return 0;  // theta lives on-chip for the whole call in every current path
+  if (rbm->dtype != NK_F32) return 0;  // generic path: theta lives in shared memory for the whole call
+  return (int64_t)(ws_theta_bytes(rbm, B) + 256 + (((size_t)B * 4 + 255) & ~(size_t)255));
 }
 
 int nk_sweep(void *stream, const nk_rbm_t *rbm, nk_chains_t *ch, const nk_sweep_t *a) {
@@ -169,13 +173,29 @@ int nk_sweep(void *stream, const nk_rbm_t *rbm, nk_chains_t *ch, const nk_sweep_
   k.eloc_out = a->eloc_out;
   k.eloc_dtype = a->eloc_dtype;
 
-  const bool fast_ok = sweep_fast_supported(k);
+  const bool fast_ok = sweep_fast_supported(k) && ch->workspace != nullptr;
   if (a->path == NK_PATH_FAST && !fast_ok) {
-    set_error("nk_sweep: NK_PATH_FAST does not support this configuration (needs LocalRule, N<=128, M<=512, N*Mpad*sizeof(T) "
-              "within shared memory, Ising or no operator)");
+    set_error("nk_sweep: NK_PATH_FAST does not support this configuration (needs fp32, LocalRule, N<=128, M%%4==0, M<=512, the "
+              "tanh table within shared memory, Ising or no operator, and a workspace of nk_sweep_workspace_bytes())");
     return NK_EUNSUPPORTED;
   }
-  rc = (a->path != NK_PATH_GENERIC && fast_ok) ? sweep_fast((cudaStream_t)stream, k) : sweep_generic((cudaStream_t)stream, k);
+  if (a->path != NK_PATH_GENERIC && fast_ok) {
+    cudaStream_t st = (cudaStream_t)stream;
+    float *theta = reinterpret_cast<float *>(ch->workspace);
+    int *flags = reinterpret_cast<int *>(reinterpret_cast<char *>(ch->workspace) + ws_theta_bytes(rbm, ch->B));
+    void *scratch = reinterpret_cast<char *>(flags) + 256;
+    NK_CUDA_OK(cudaMemsetAsync(flags, 0, 256, st));
+    rc = theta_gemm(st, *rbm, ch->sigma, ch->B, theta, scratch);  // theta = sigma W + b  (the only dense contraction)
+    if (rc) return rc;
+    rc = sweep_fast(st, k, theta, flags);
+    if (rc == NK_OK && a->path == NK_PATH_AUTO) {
+      // weights beyond the product form's range: the fast kernel raises flags[0] and exits; this one then runs
+      k.run_if_flag = flags;
+      rc = sweep_generic(st, k);
+    }
+  } else {
+    rc = sweep_generic((cudaStream_t)stream, k);
+  }
   if (rc == NK_OK) ch->t += (uint64_t)(a->n_discard + a->chain_length) * (uint64_t)a->sweep_size;
   return rc;
 }

@@ -29,12 +29,13 @@ struct SweepKernelArgs {
   void *eloc_out;
   int32_t eloc_dtype;
   int32_t n_pad;  // per-warp sigma stride in smem
+  const int *run_if_flag;  // generic kernel only: run iff NULL or *run_if_flag != 0 (fast-path hand-over)
 };
 
 // sweep_generic.cu — theta-form path (any shape / dtype / rule)
 int sweep_generic(cudaStream_t stream, const SweepKernelArgs &a);
 // sweep_fast.cu — product-form path (fp32 LocalRule, tanh table resident in shared memory)
 bool sweep_fast_supported(const SweepKernelArgs &a);
-int sweep_fast(cudaStream_t stream, const SweepKernelArgs &a);
+int sweep_fast(cudaStream_t stream, const SweepKernelArgs &a, const float *theta_ws, int *flags);
 
 }  // namespace nk

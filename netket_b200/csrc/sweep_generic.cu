@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(256) sweep_generic_kernel(const __grid_constan
   int8_t *sig = reinterpret_cast<int8_t *>(smem_raw + (size_t)warps * M * sizeof(T)) + (size_t)warp * p.n_pad;
   const T pw = (T)p.machine_pow;
   const int64_t T_total = (int64_t)(p.n_discard + p.chain_length) * p.sweep_size;
+  if (p.run_if_flag != nullptr && *p.run_if_flag == 0) return;  // the fast kernel did the work
 
   for (int64_t chain = (int64_t)blockIdx.x * warps + warp; chain < p.B; chain += (int64_t)gridDim.x * warps) {
     for (int i = lane; i < N; i += 32) sig[i] = p.sigma[chain * N + i];

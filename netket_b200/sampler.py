@@ -187,6 +187,18 @@ class MetropolisSampler:
                 f"{type(machine).__name__}: the fused sampler recognises netket_b200.models.RBM only "
                 "(no generic apply-function path, no CPU fallback)")
 
+    def _workspace(self, rbm, B, device):
+        """Scratch for the fast path (theta from the GEMM + hand-over flag), cached per (shape, device)."""
+        nbytes = int(_lib.lib().nk_sweep_workspace_bytes(C.byref(rbm), B))
+        if nbytes <= 0:
+            return None
+        key = (str(device), nbytes)
+        cache = self.__dict__.setdefault("_ws_cache", {})
+        if key not in cache:
+            cache.clear()
+            cache[key] = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        return cache[key]
+
     def _random_state(self, seed, chain_offset, device):
         return self.hilbert.random_state(seed, self.n_chains_per_rank, chain_offset=chain_offset, device=device)
 
@@ -236,8 +248,10 @@ class MetropolisSampler:
         nacc = state.n_accepted_proc.clone()
         log_prob = torch.empty((B,), dtype=W.dtype, device=dev)
         seed, t = state.rng
+        ws = self._workspace(rbm, B, dev) if path != _lib.NK_PATH_GENERIC else None
         chains = _lib.nk_chains_t(sigma=sigma.data_ptr(), log_prob=log_prob.data_ptr(), n_accepted=nacc.data_ptr(),
-                                  workspace=None, B=B, seed=seed, t=t, chain_offset=state.chain_offset)
+                                  workspace=ws.data_ptr() if ws is not None else None, B=B, seed=seed, t=t,
+                                  chain_offset=state.chain_offset)
         samples = torch.empty((B, chain_length, N), dtype=torch.int8, device=dev) if want_samples else None
         logp = torch.empty((B, chain_length), dtype=W.dtype, device=dev) if return_log_probabilities else None
         a = _lib.nk_sweep_t()

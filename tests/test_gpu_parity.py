@@ -377,3 +377,95 @@ def test_statistics(cuda, shape, dtype):
     for k in ("mean", "variance", "error_of_mean", "tau_corr", "R_hat"):
         np.testing.assert_allclose(getattr(st, k), ref[k], rtol=tol, atol=1e-12, equal_nan=True, err_msg=k)
     assert set(st.to_dict()) == {"Mean", "Variance", "Sigma", "R_hat", "TauCorr"}
+
+
+# ----------------------------------------------------------------------------------------- fast (product-form) path
+def _fast_case(nk, L, n_dim, alpha, std, B, h=3.0, seed=15324):
+    g = nk.graph.Hypercube(L, n_dim)
+    N = g.n_nodes
+    hi = nk.hilbert.Spin(0.5, N)
+    (W, b, a), var = _params(N, alpha, np.float32, std)
+    model = nk.models.RBM(alpha=alpha, param_dtype=np.float32)
+    sa = nk.sampler.MetropolisLocal(hi, n_chains=B)
+    op = nk.operator.Ising(hi, g, h=h)
+    e, _ = ograph.hypercube_edges(L, n_dim)
+    return g, hi, (W, b, a), var, model, sa, op, e
+
+
+@pytest.mark.parametrize("L,n_dim,alpha,std", [(10, 2, 4, 0.01), (10, 2, 4, 0.1), (20, 1, 1, 0.3), (4, 2, 2, 0.05), (6, 2, 3, 0.02), (5, 2, 4, 0.2)])
+def test_fast_sweep_follows_oracle_chain(cuda, L, n_dim, alpha, std):
+    """Same Philox stream => same chains as the oracle except at fp32 accept-boundary ties."""
+    nk = _nk()
+    B, CL = 96, 2
+    g, hi, (W, b, a), var, model, sa, op, e = _fast_case(nk, L, n_dim, alpha, std, B)
+    st = sa.init_state(model, var, seed=7)
+    seed, t0 = st.rng
+    ref = osampler.sample_chain("local", st.σ.cpu().numpy(), W.astype(np.float64), b.astype(np.float64), a.astype(np.float64),
+                                chain_length=CL, seed=seed, t0=t0,
+                                stream=None if True else None)
+    # the oracle above runs in fp64 but must see the fp32 uniforms: rebuild the stream explicitly
+    words, u32 = orng.proposal_stream(seed, t0, CL * hi.size, np.arange(B), np.float32)
+    ref = osampler.sample_chain("local", st.σ.cpu().numpy(), W.astype(np.float64), b.astype(np.float64), a.astype(np.float64),
+                                chain_length=CL, stream=(words[..., 0], u32.astype(np.float64)))
+    (samples, logp), st2 = sa.sample(model, var, state=st, chain_length=CL, return_log_probabilities=True, _path=2)
+    same = np.all(samples.cpu().numpy() == ref["samples"], axis=(1, 2))
+    assert same.mean() >= 0.9, same.mean()
+    np.testing.assert_allclose(logp.cpu().numpy()[same], ref["log_prob_samples"][same], rtol=2e-5, atol=2e-4)
+    assert np.array_equal(st2.n_accepted_proc.cpu().numpy()[same], ref["n_accepted"][same])
+    np.testing.assert_allclose(st2.log_prob.cpu().numpy()[same], ref["log_prob"][same], rtol=2e-5, atol=2e-4)
+    assert np.array_equal(st2.σ.cpu().numpy(), samples[:, -1].cpu().numpy())
+
+
+@pytest.mark.parametrize("L,n_dim,alpha,std,CL", [(10, 2, 4, 0.01, 4), (10, 2, 4, 0.1, 4), (10, 2, 4, 0.05, 48), (4, 2, 2, 0.3, 8), (20, 1, 1, 0.2, 8)])
+def test_fast_fused_eloc_matches_oracle(cuda, L, n_dim, alpha, std, CL):
+    """E_loc produced inside the fast sweep kernel vs the oracle's materialised E_loc on the same samples (1e-5);
+    CL=48 checks that the (C,S) recurrences do not drift over ~5000 proposals."""
+    nk = _nk()
+    B = 48
+    g, hi, (W, b, a), var, model, sa, op, e = _fast_case(nk, L, n_dim, alpha, std, B)
+    st = sa.init_state(model, var, seed=11)
+    samples, _, eloc, st2 = sa._launch(model, var, st, CL, n_discard=1, operator=op, path=2)
+    ref = oest.local_estimators(samples.cpu().numpy(), lambda x: oops.ising_conn_padded(x, e, op.h, op.J), W.astype(np.float64),
+                                b.astype(np.float64), a.astype(np.float64))
+    assert eloc.dtype == torch.float64
+    np.testing.assert_allclose(eloc.cpu().numpy(), ref, rtol=1e-5, atol=1e-5 * np.abs(ref).max())
+    # and the generic kernel's stand-alone E_loc agrees as well
+    vs = nk.vqs.MCState(sa, model, variables=var, n_samples=B, seed=1)
+    alone = vs._eloc_on_samples(op, samples, path=1)
+    np.testing.assert_allclose(eloc.cpu().numpy(), alone.cpu().numpy(), rtol=2e-5, atol=2e-5 * np.abs(ref).max())
+
+
+def test_fast_path_hands_over_to_generic_for_large_weights(cuda):
+    """max|tanh 2W| beyond the product form's range: NK_PATH_AUTO must give exactly the generic kernel's chains."""
+    nk = _nk()
+    g, hi, (W, b, a), var, model, sa, op, e = _fast_case(nk, 4, 2, 2, 1.5, 32)
+    assert np.abs(np.tanh(2 * W)).max() > 0.99
+    st = sa.init_state(model, var, seed=3)
+    s_auto, _, e_auto, st_a = sa._launch(model, var, st, 3, operator=op, path=0)
+    s_gen, _, e_gen, st_g = sa._launch(model, var, st, 3, operator=op, path=1)
+    assert np.array_equal(s_auto.cpu().numpy(), s_gen.cpu().numpy())
+    assert np.array_equal(e_auto.cpu().numpy(), e_gen.cpu().numpy())
+    assert np.array_equal(st_a.n_accepted_proc.cpu().numpy(), st_g.n_accepted_proc.cpu().numpy())
+
+
+@pytest.mark.parametrize("std", [0.01, 0.4])
+def test_fast_sampler_chi_square(cuda, std):
+    """test/sampler/test_sampler.py:399-457 on the fast path: histogram vs exact |psi|^2 (4 sites, M = 8)."""
+    from scipy import stats as sstats
+
+    nk = _nk()
+    N = 4
+    hi = nk.hilbert.Spin(0.5, N)
+    (W, b, a), var = _params(N, 2, np.float32, std)
+    model = nk.models.RBM(alpha=2, param_dtype=np.float32)
+    sa = nk.sampler.MetropolisLocal(hi, n_chains=512, sweep_size=8)
+    st = sa.init_state(model, var, seed=5)
+    samples, _, _, st2 = sa._launch(model, var, st, 100, n_discard=20, path=2)
+    p = osampler.exact_distribution(W, b, a, ohilbert.all_states(N))
+    counts = np.bincount(ohilbert.states_to_numbers(samples.cpu().numpy().reshape(-1, N), N), minlength=16)
+    # chains are autocorrelated: thin to every 4th sweep before the chi-square
+    thin = samples[:, ::4].cpu().numpy().reshape(-1, N)
+    counts = np.bincount(ohilbert.states_to_numbers(thin, N), minlength=16)
+    pv = sstats.chisquare(counts, p * counts.sum()).pvalue
+    assert pv > 1e-3, pv
+    assert 0.0 < st2.acceptance <= 1.0
