@@ -194,6 +194,10 @@ int nk_ctx_step_host(nk_ctx *ctx, const void *W_host, const void *b_host, const 
 /* copy the current configurations sigma [n_chains, N] to host */
 int nk_ctx_get_sigma_host(nk_ctx *ctx, int8_t *sigma_host);
 
+/* Measurement utility (synchronises): on-chip peak rates of the current device, used as roofline denominators.
+ * which: 0 shared-memory read GB/s (LDS.128), 1 L2 read GB/s, 2 fp32 FMA GFLOP/s, 3 MUFU Gop/s, 4 fp64 FMA GFLOP/s. */
+int nk_microbench(int32_t which, double *result_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libnkb200.so")
+LIB_PATH = os.environ.get("NKB200_LIB") or os.path.join(_HERE, "lib", "libnkb200.so")  # env override: developer A/B builds
 
 NK_F32, NK_F64 = 0, 1
 NK_RULE_LOCAL, NK_RULE_EXCHANGE = 0, 1
@@ -84,6 +84,7 @@ SYMBOLS = {
     "nk_ctx_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                    C.POINTER(C.c_double)]),
     "nk_ctx_get_sigma_host": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "nk_microbench": (C.c_int, [C.c_int32, C.POINTER(C.c_double)]),
 }
 
 _lib = None

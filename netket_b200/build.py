@@ -23,7 +23,7 @@ NVCC_FLAGS = [
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "-I", INCLUDE, "-I", CSRC,
-]
+] + os.environ.get("NKB200_NVCC_FLAGS", "").split()
 
 
 def _nvcc():

@@ -1,24 +1,25 @@
-// Product-form fast path of the Metropolis sweep (fp32, LocalRule, tanh table resident in shared memory),
+// Product-form fast path of the Metropolis sweep (fp32, LocalRule, weight table resident in shared memory),
 // optionally fused with the transverse-field-Ising local energy.
 //
 // Replaces the hot loop of netket/sampler/metropolis.py:427-462 (+ rules/local.py:40-49) and, when fused,
 // netket/vqs/mc/kernels.py:62-71 with netket/operator/_ising/jax.py:125-165.
 //
-// Math.  With t_j = tanh(theta_j), tau_ij = tanh(2 W_ij), nu = -sigma_i:
-//     cosh(theta_j + 2 nu W_ij) / cosh(theta_j) = cosh(2 W_ij) * (1 + nu tau_ij t_j)
-// so a single-flip log-ratio is
-//     delta_i = 2 nu a_i + sum_j log cosh(2 W_ij) + log prod_j (1 + nu tau_ij t_j).
-// Each hidden unit is carried as an *unnormalised* pair (C_j, S_j) ~ (cosh theta_j, sinh theta_j):
-//     proposal:  C'_j = C_j + nu tau_ij S_j            (1 FFMA)   and   prod_j C'_j   (1 FMUL)
-//     accept:    S'_j = S_j + nu tau_ij C_j, C_j <- C'_j
-// i.e. no transcendental per (proposal, hidden unit): one lg2 per lane per proposal, one division per hidden unit
-// every `renorm` proposals (the period is chosen from max|tau| so that no lane product can leave the fp32 range).
+// Math ("exponential form").  Each hidden unit is carried as an unnormalised positive pair
+//     (A_j, B_j)  proportional to  (exp(theta_j), exp(-theta_j)),     cosh(theta_j) ~ (A_j + B_j) / 2,
+// and the weight table is G_ij = exp(-4 W_ij).  Flipping site i changes theta_j by 2 nu W_ij, nu = -sigma_i:
+//     nu = +1:  cosh(theta'_j) ~ exp(2 W_ij) (A_j + B_j G_ij) / 2      accept:  B_j <- B_j G_ij
+//     nu = -1:  cosh(theta'_j) ~ exp(2 W_ij) (A_j G_ij + B_j) / 2      accept:  A_j <- A_j G_ij
+// so  delta_i = 2 nu a_i + 2 sum_j W_ij + log prod_j (A_j + B_j G_ij | A_j G_ij + B_j) - log prod_j (A_j + B_j).
+// Per (proposal, hidden unit) that is one FFMA and one FMUL, no transcendental and - every term being positive -
+// no cancellation, however saturated the unit is; the accept costs one FMUL.  Two lg2 per lane per proposal turn the
+// lane products into a sum; (A, B) are renormalised to A + B = 1 every `renorm` proposals, a period chosen from
+// max|W| so that no lane product can leave the fp32 range.
 // One warp owns one chain for the whole call; lanes own hidden units (packed as float2 -> FFMA2/FMUL2);
-// W is brought in once per CTA by TMA bulk copies and turned into the tau table in place.
-// The binding resource is the shared-memory read of one tau row (M floats) per proposal per chain.
+// W is brought in once per CTA by TMA bulk copies and turned into the G table in place.
+// The binding resource is the shared-memory read of one G row (M floats) per proposal per chain.
 //
-// Validity: max|tau| <= TAU_LIMIT (|W| < ~0.97); otherwise the kernel raises a device flag and the theta-form
-// generic kernel, always enqueued behind it, does the work (no host round trip).
+// Validity: 8 * (4 max|W| log2 e) * 2 <= 120 (|W| <~ 1.3); otherwise the kernel raises a device flag and the
+// theta-form generic kernel, always enqueued behind it, does the work (no host round trip).
 #include "kernels.cuh"
 
 namespace nk {
@@ -66,46 +67,127 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
                : "memory");
 }
 
-constexpr int FAST_WARPS = 24;
+#ifndef NK_FAST_WARPS
+#define NK_FAST_WARPS 20
+#endif
+constexpr int FAST_WARPS = NK_FAST_WARPS;
 constexpr int FAST_THREADS = FAST_WARPS * 32;
-constexpr float TAU_LIMIT = 0.96f;
+constexpr float EXP_RANGE = 120.0f;  // log2 headroom allowed for a lane product
+constexpr float FX_SCALE = 524288.0f;            // 2^19: fixed-point scale of per-lane log2 partials (REDUX add)
+constexpr float FX_INV = 1.0f / 524288.0f;
+
+// ---- explicit shared-space accesses (32-bit shared addresses kept in registers; no generic-address arithmetic)
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float2 lds64(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lg2_fast(float x) {  // x is a positive normal number by construction
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 template <int NFULL, int TAIL>
 struct Lanes {
   static constexpr int NE = 4 * NFULL + TAIL;        // hidden units per lane
   static constexpr int NP = (NE + 1) / 2;            // float2 pairs per lane
-  static constexpr int MP = 128 * NFULL + 32 * TAIL; // padded row length of the tau table (floats)
+  static constexpr int MP = 128 * NFULL + 32 * TAIL; // padded row length of the G table (floats)
   // hidden-unit index of element e of this lane (may be >= M: padding)
   static __device__ __forceinline__ int unit(int e, int lane) {
     return e < 4 * NFULL ? 128 * (e >> 2) + 4 * lane + (e & 3) : 128 * NFULL + TAIL * lane + (e - 4 * NFULL);
   }
-  static __device__ __forceinline__ void load_row(const float *row, int lane, float2 (&t2)[NP]) {
+  // row_lane = shared address of G[i][0] + 16 * lane ; tail_lane = shared address of G[i][128*NFULL + TAIL*lane]
+  static __device__ __forceinline__ void load_row(uint32_t row_lane, uint32_t tail_lane, float2 (&g2)[NP]) {
 #pragma unroll
     for (int q = 0; q < NFULL; ++q) {
-      const float4 v = *reinterpret_cast<const float4 *>(row + 128 * q + 4 * lane);
-      t2[2 * q] = make_float2(v.x, v.y);
-      t2[2 * q + 1] = make_float2(v.z, v.w);
+      const float4 v = lds128(row_lane + 512 * q);
+      g2[2 * q] = make_float2(v.x, v.y);
+      g2[2 * q + 1] = make_float2(v.z, v.w);
     }
-    if (TAIL == 1) t2[2 * NFULL] = make_float2(row[128 * NFULL + lane], 0.0f);
-    if (TAIL == 2) t2[2 * NFULL] = *reinterpret_cast<const float2 *>(row + 128 * NFULL + 2 * lane);
+    if (TAIL == 1) g2[2 * NFULL] = make_float2(lds32(tail_lane), 1.0f);  // odd element count: neutral partner (G = 1)
+    if (TAIL == 2) g2[2 * NFULL] = lds64(tail_lane);
   }
 };
 
-struct FastSmem {
-  float *tau;     // [N][MP]
-  float *lcrow;   // [N]  sum_j log cosh(2 W_ij)
-  float *a2;      // [N]  2 a_i (0 without visible bias)
-  uint8_t *edges; // [E][2]
-  uint64_t *bar;
-  float *red;     // [32]
+__host__ __device__ inline size_t fast_smem_bytes(int N, int MP, int E) {
+  size_t s = (size_t)N * MP * 4;            // G table
+  s += (size_t)N * 16;                      // per-site constants {x = log2e 2 sum_j W_ij, y = log2e 2 a_i, fix(x+y), fix(x-y)}
+  s += ((size_t)2 * E + 15) & ~(size_t)15;  // edges (uint8 pairs)
+  s += 16 + 32 * 4;                         // mbarrier, reduction scratch
+  return s;
+}
+
+__device__ __forceinline__ uint32_t sw4sel(const uint32_t (&w)[4], int i) {
+  return (i < 2) ? ((i == 0) ? w[0] : w[1]) : ((i == 2) ? w[2] : w[3]);
+}
+
+// Per-chain registers of one warp.
+template <int NP>
+struct ChainRegs {
+  float2 A2[NP], B2[NP];
+  int R;              // fixed-point log2 prod_j (A_j + B_j), summed over the warp
+  uint32_t mybits;    // bit b of lane l: sigma of site 32 b + l is -1
+  uint32_t nacc;
+  int since;          // accepted moves since the last renormalisation
 };
 
-__host__ __device__ inline size_t fast_smem_bytes(int N, int MP, int E) {
-  size_t s = (size_t)N * MP * 4;
-  s += (size_t)N * 4 * 2;
-  s += ((size_t)2 * E + 15) & ~(size_t)15;
-  s += 16 + 32 * 4;
-  return s;
+// lane product prod_q c_q.x * c_q.y with c = X * g + Y
+template <int NP>
+__device__ __forceinline__ float lane_product(const float2 (&X)[NP], const float2 (&Y)[NP], const float2 (&g2)[NP]) {
+  float2 Pa = ffma2(X[0], g2[0], Y[0]);
+  float2 Pb = make_float2(1.0f, 1.0f);
+  if (NP > 1) Pb = ffma2(X[1], g2[1], Y[1]);
+#pragma unroll
+  for (int q = 2; q < NP; ++q) {
+    const float2 c = ffma2(X[q], g2[q], Y[q]);
+    if (q & 1)
+      Pb = fmul2(Pb, c);
+    else
+      Pa = fmul2(Pa, c);
+  }
+  return NP > 1 ? (Pa.x * Pa.y) * (Pb.x * Pb.y) : Pa.x * Pa.y;
+}
+
+// One Metropolis proposal on site `site` whose spin has sign POS ? -1 : +1 (nu = -sigma = POS ? +1 : -1).
+// Everything after the lane product is integer: with S = FX_SCALE,
+//   fix(log2 ratio) = (Rp - R) + fix(log2e (2 sum_j W_ij + 2 nu a_i))      and      thr = fix(log2(u) / machine_pow),
+// accept = u < exp(machine_pow * delta)  <=>  thr < fix(log2 ratio)         (netket/sampler/metropolis.py:444-450).
+// Returns true if the state must be renormalised before the next proposal.
+template <int NP, bool POS>
+__device__ __forceinline__ bool propose(ChainRegs<NP> &c, const float2 (&g2)[NP], int rcfix, int thr, int site, int lane) {
+  const float P = POS ? lane_product<NP>(c.B2, c.A2, g2) : lane_product<NP>(c.A2, c.B2, g2);
+  const int Rp = __reduce_add_sync(0xffffffffu, __float2int_rn(lg2_fast(P) * FX_SCALE));
+  if (thr < (int)((uint32_t)Rp - (uint32_t)c.R + (uint32_t)rcfix)) {
+    if (POS) {
+#pragma unroll
+      for (int q = 0; q < NP; ++q) c.B2[q] = fmul2(c.B2[q], g2[q]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < NP; ++q) c.A2[q] = fmul2(c.A2[q], g2[q]);
+    }
+    c.R = Rp;
+    ++c.nacc;
+    ++c.since;
+    if (lane == (site & 31)) c.mybits ^= 1u << (site >> 5);
+    return true;
+  }
+  return false;
 }
 
 template <int NFULL, int TAIL>
@@ -115,235 +197,288 @@ __global__ void __launch_bounds__(FAST_THREADS, 1)
   constexpr int NP = LM::NP, NE = LM::NE, MP = LM::MP;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int N = p.rbm.N, M = p.rbm.M, E = p.eloc_kind == 1 ? p.ising.n_edges : 0;
-  FastSmem sm;
-  sm.tau = reinterpret_cast<float *>(smem_raw);
-  sm.lcrow = sm.tau + (size_t)N * MP;
-  sm.a2 = sm.lcrow + N;
-  sm.edges = reinterpret_cast<uint8_t *>(sm.a2 + N);
-  sm.bar = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(sm.edges) + (((size_t)2 * E + 15) & ~(size_t)15));
-  sm.red = reinterpret_cast<float *>(sm.bar + 2);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float *Gtab = reinterpret_cast<float *>(smem_raw);
+  float4 *rctab = reinterpret_cast<float4 *>(Gtab + (size_t)N * MP);
+  uint8_t *edges = reinterpret_cast<uint8_t *>(rctab + N);
+  uint64_t *bar = reinterpret_cast<uint64_t *>(edges + (((size_t)2 * E + 15) & ~(size_t)15));
+  float *red = reinterpret_cast<float *>(bar + 2);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform by construction: lets ptxas use uniform control flow
   const float *W = reinterpret_cast<const float *>(p.rbm.W);
   const float *avis = reinterpret_cast<const float *>(p.rbm.a);
+  const float LOG2E = 1.4426950408889634f, LN2 = 0.69314718055994530942f;
 
   // ---------------- stage W into shared memory with TMA bulk copies (one per row: rows are padded to MP floats)
   if (tid == 0) {
-    mbar_init(sm.bar, 1);
+    mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   if (tid == 0) {
-    mbar_expect_tx(sm.bar, (uint32_t)((size_t)N * M * 4));
-    for (int i = 0; i < N; ++i) tma_bulk_g2s(sm.tau + (size_t)i * MP, W + (size_t)i * M, (uint32_t)(M * 4), sm.bar);
+    mbar_expect_tx(bar, (uint32_t)((size_t)N * M * 4));
+    for (int i = 0; i < N; ++i) tma_bulk_g2s(Gtab + (size_t)i * MP, W + (size_t)i * M, (uint32_t)(M * 4), bar);
   }
-  for (int i = tid; i < N; i += FAST_THREADS) sm.a2[i] = avis != nullptr ? 2.0f * avis[i] : 0.0f;
-  for (int e = tid; e < 2 * E; e += FAST_THREADS) sm.edges[e] = (uint8_t)p.ising.edges[e];
-  mbar_wait(sm.bar, 0);
-  // ---------------- W -> tau = tanh(2W) in place; row constants; max|tau|
-  float tmax = 0.0f;
+  for (int e = tid; e < 2 * E; e += FAST_THREADS) edges[e] = (uint8_t)p.ising.edges[e];
+  mbar_wait(bar, 0);
+  // ---------------- W -> G = exp(-4W) in place; per-site constants; max|W|
+  float wmax = 0.0f;
   for (int i = warp; i < N; i += FAST_WARPS) {
-    float *row = sm.tau + (size_t)i * MP;
-    float lc = 0.0f;
+    float *row = Gtab + (size_t)i * MP;
+    float rs = 0.0f;
     for (int j = lane; j < MP; j += 32) {
-      float tv = 0.0f;
+      float gv = 1.0f;  // padding: A + B*1 / A*1 + B leave the products unchanged up to the common factor (A+B)
       if (j < M) {
-        const float w2 = 2.0f * row[j];
-        tv = tanhf(w2);
-        lc += lncosh(w2);
-        tmax = fmaxf(tmax, fabsf(tv));
+        const float w = row[j];
+        gv = expf(-4.0f * w);
+        rs += w;
+        wmax = fmaxf(wmax, fabsf(w));
       }
-      row[j] = tv;
+      row[j] = gv;
     }
-    lc = warp_sum(lc);
-    if (lane == 0) sm.lcrow[i] = lc;
+    rs = warp_sum(rs);
+    if (lane == 0) {
+      const float x = LOG2E * 2.0f * rs, y = avis != nullptr ? LOG2E * 2.0f * avis[i] : 0.0f;
+      rctab[i] = make_float4(x, y, __int_as_float(__float2int_rn((x + y) * FX_SCALE)), __int_as_float(__float2int_rn((x - y) * FX_SCALE)));
+    }
   }
 #pragma unroll
-  for (int m = 16; m > 0; m >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, m));
-  if (lane == 0) sm.red[warp] = tmax;
+  for (int m = 16; m > 0; m >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, m));
+  if (lane == 0) red[warp] = wmax;
   __syncthreads();
-  tmax = 0.0f;
-  for (int w = 0; w < FAST_WARPS; ++w) tmax = fmaxf(tmax, sm.red[w]);
-  // renormalisation period: NE * (r + 1) * max(log2(1+tmax), -log2(1-tmax)) must stay below the fp32 exponent range
+  wmax = 0.0f;
+  for (int w = 0; w < FAST_WARPS; ++w) wmax = fmaxf(wmax, red[w]);
+  // renormalisation period r: a lane product has 2*NP factors, each within G^(+-(r+1)) of 1 after r un-normalised
+  // accepts, so 2 NP (r + 1) 4 wmax log2(e) must stay below the fp32 exponent range (and 32 lanes of it, times
+  // FX_SCALE, inside int32)
   int renorm = 0;
-  if (tmax <= TAU_LIMIT) {
-    const float per = (float)NE * fmaxf(log2f(1.0f + tmax), -log2f(1.0f - tmax));
+  {
+    const float per = (float)(2 * NP) * 4.0f * wmax * LOG2E;
     renorm = 32;
-    while (renorm >= 1 && (float)(renorm + 1) * per > 120.0f) renorm >>= 1;
+    while (renorm >= 1 && (float)(renorm + 1) * per > EXP_RANGE) renorm >>= 1;
+    if (!(wmax < 1.0e30f)) renorm = 0;  // NaN / Inf weights
   }
   if (renorm < 1) {  // weights too large for the product form: hand over to the generic kernel queued behind us
     if (blockIdx.x == 0 && tid == 0) flags[0] = 1;
     return;
   }
-  const int rmask = renorm - 1;
-
-  const float pw = (float)p.machine_pow;
-  const float inv_pw = pw > 0.0f ? 1.0f / pw : 0.0f;
-  const int64_t T_total = (int64_t)(p.n_discard + p.chain_length) * p.sweep_size;
-  const float LN2 = 0.69314718055994530942f;
+  
+  const int T_total = (p.n_discard + p.chain_length) * p.sweep_size;
   const float hh = (float)p.ising.h, JJ = (float)p.ising.J;
+  // loop-invariant values the hot loop needs, made opaque so that they stay in registers instead of being
+  // rematerialised (S2R + LEA + constant-bank loads) on every proposal
+  float pw = (float)p.machine_pow;
+  const float inv_pw = pw > 0.0f ? 1.0f / pw : 0.0f;
+  uint32_t rc_s = smem_u32(rctab);
+  uint32_t lane_row = smem_u32(Gtab) + 16u * lane;                         // + site * MP * 4
+  uint32_t lane_tail = smem_u32(Gtab) + 512u * NFULL + 4u * TAIL * lane;   // + site * MP * 4
+  int sweep_size = p.sweep_size;
+  int lane_o = lane;
+  asm volatile("" : "+r"(rc_s), "+r"(lane_row), "+r"(lane_tail), "+r"(sweep_size), "+r"(lane_o));
 
-  for (int64_t chain = (int64_t)blockIdx.x * FAST_WARPS + warp; chain < p.B; chain += (int64_t)gridDim.x * FAST_WARPS) {
-    // ---- sigma as a bit mask (bit = 1 <=> sigma = -1), replicated in every lane
-    uint32_t sb[4];
+  for (int chain = blockIdx.x * FAST_WARPS + warp; chain < (int)p.B; chain += gridDim.x * FAST_WARPS) {
+    ChainRegs<NP> c;
+    // ---- sigma, lane-distributed: lane l keeps the bits of sites l, 32 + l, 64 + l, 96 + l
+    c.mybits = 0;
 #pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      const int idx = 32 * w + lane;
-      const bool neg = idx < N && p.sigma[chain * N + idx] < 0;
-      sb[w] = __ballot_sync(0xffffffffu, neg);
+    for (int b = 0; b < 4; ++b) {
+      const int idx = 32 * b + lane;
+      if (idx < N && p.sigma[(size_t)chain * N + idx] < 0) c.mybits |= 1u << b;
     }
-    // ---- theta (from the GEMM) -> (C, S) = (1, tanh theta); logpsi
-    float2 C2[NP], S2[NP];
-    float lc = 0.0f;
+    // ---- theta (from the GEMM) -> (A, B) = (e^theta, e^-theta) / (2 cosh theta)
     {
       const float *th = theta_ws + (size_t)chain * M;
 #pragma unroll
       for (int e = 0; e < 2 * NP; ++e) {
         const int j = e < NE ? LM::unit(e, lane) : M;
-        float tv = 0.0f;
+        float av = 0.5f, bv = 0.5f;  // padding units: theta = 0
         if (j < M) {
           const float x = th[j];
-          tv = tanhf(x);
-          lc += lncosh(x);
+          const float ex = expf(-2.0f * fabsf(x));
+          const float big = 1.0f / (1.0f + ex), small = ex * big;
+          av = x >= 0.0f ? big : small;
+          bv = x >= 0.0f ? small : big;
         }
-        if (e & 1)
-          S2[e >> 1].y = tv;
-        else
-          S2[e >> 1].x = tv;
+        if (e & 1) {
+          c.A2[e >> 1].y = av;
+          c.B2[e >> 1].y = bv;
+        } else {
+          c.A2[e >> 1].x = av;
+          c.B2[e >> 1].x = bv;
+        }
       }
-#pragma unroll
-      for (int q = 0; q < NP; ++q) C2[q] = make_float2(1.0f, 1.0f);
     }
-    for (int i = lane; i < N; i += 32) {
-      const float s = ((sb[i >> 5] >> (i & 31)) & 1u) ? -1.0f : 1.0f;
-      lc = fmaf(0.5f * sm.a2[i], s, lc);
-    }
-    float logpsi = warp_sum(lc);
-    float R = 0.0f;  // log2 prod_j C_j
-    int64_t nacc = 0;
-    int in_sweep = 0;
-    int64_t sweep_idx = 0;
+    c.R = 0;
+    c.nacc = 0;
+    c.since = 0;
+    int in_sweep = 0, sweep_idx = 0;
     const uint64_t gchain = p.chain_offset + (uint64_t)chain;
 
-    auto renormalise = [&]() {
+    auto renormalise = [&]() {  // A + B = 1
 #pragma unroll
       for (int q = 0; q < NP; ++q) {
-        S2[q].x = __fdividef(S2[q].x, C2[q].x);
-        S2[q].y = __fdividef(S2[q].y, C2[q].y);
-        C2[q] = make_float2(1.0f, 1.0f);
+        const float ix = __frcp_rn(c.A2[q].x + c.B2[q].x), iy = __frcp_rn(c.A2[q].y + c.B2[q].y);
+        c.A2[q] = fmul2(c.A2[q], make_float2(ix, iy));
+        c.B2[q] = fmul2(c.B2[q], make_float2(ix, iy));
       }
-      R = 0.0f;
+      c.R = 0;
+      c.since = 0;
     };
-    // log2 prod_j (C_j + nu tau_ij S_j), reduced over the warp
-    auto row_log2 = [&](const float2(&t2)[NP], bool nu_pos) -> float {
-      float2 Pa = make_float2(1.0f, 1.0f), Pb = make_float2(1.0f, 1.0f);
-      if (nu_pos) {
+    // log psi of the current state from (A, B): lncosh(theta_j) = log((A_j + B_j) / (2 sqrt(A_j B_j)))
+    auto logpsi_now = [&]() -> float {
+      float acc2 = 0.0f;  // log2 units
 #pragma unroll
-        for (int q = 0; q < NP; ++q) {
-          const float2 c = ffma2(t2[q], S2[q], C2[q]);
-          if (q & 1)
-            Pb = fmul2(Pb, c);
-          else
-            Pa = fmul2(Pa, c);
-        }
-      } else {
-#pragma unroll
-        for (int q = 0; q < NP; ++q) {
-          const float2 c = ffma2(neg2(t2[q]), S2[q], C2[q]);
-          if (q & 1)
-            Pb = fmul2(Pb, c);
-          else
-            Pa = fmul2(Pa, c);
-        }
+      for (int q = 0; q < NP; ++q) {
+        acc2 += log2f(c.A2[q].x + c.B2[q].x) - 0.5f * (log2f(c.A2[q].x) + log2f(c.B2[q].x)) - 1.0f;
+        acc2 += log2f(c.A2[q].y + c.B2[q].y) - 0.5f * (log2f(c.A2[q].y) + log2f(c.B2[q].y)) - 1.0f;
       }
-      const float2 P = fmul2(Pa, Pb);
-      return warp_sum(__log2f(P.x * P.y));
+      float vis2 = 0.0f;  // log2e * sum_i a_i sigma_i
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int idx = 32 * b + lane;
+        if (idx < N) vis2 += ((c.mybits >> b) & 1u) ? -0.5f * rctab[idx].y : 0.5f * rctab[idx].y;
+      }
+      return LN2 * warp_sum(acc2 + vis2);
     };
 
-    for (int64_t tt = 0; tt < T_total; tt += 32) {
-      // ---- 32 proposals' worth of randomness, one Philox call per lane
-      int site_l = 0;
-      float thr_l = 0.0f;
+    for (int tt = 0; tt < T_total; tt += 32) {
+      // ---- 32 proposals' worth of randomness, one Philox call per lane: site and thr = fix(log2(u) / machine_pow)
+      int site_l = 0, thr_l = 0;
       if (tt + lane < T_total) {
         uint32_t w0;
         float u;
         if (p.stream_w0 != nullptr) {
-          w0 = p.stream_w0[(tt + lane) * p.B + chain];
-          u = reinterpret_cast<const float *>(p.stream_u)[(tt + lane) * p.B + chain];
+          w0 = p.stream_w0[(size_t)(tt + lane) * p.B + chain];
+          u = reinterpret_cast<const float *>(p.stream_u)[(size_t)(tt + lane) * p.B + chain];
         } else {
           const uint4 w = philox_words(p.seed, p.t0 + (uint64_t)(tt + lane), gchain, STREAM_STEP);
           w0 = w.x;
           u = uniform_from_words<float>(w);
         }
         site_l = (int)__umulhi(w0, (uint32_t)N);
-        // accept = u < exp(pw * delta)  <=>  log(u) / pw < delta      (metropolis.py:444-450)
-        thr_l = pw > 0.0f ? logf(u) * inv_pw : -INFINITY;
+        // u == 0 or machine_pow == 0: always accept
+        const float t2 = (pw > 0.0f && u > 0.0f) ? log2f(u) * inv_pw * FX_SCALE : -2.0e9f;
+        thr_l = __float2int_rn(fmaxf(t2, -2.0e9f));
       }
-      const int nb = (int)min((int64_t)32, T_total - tt);
-      for (int k = 0; k < nb; ++k) {
-        if ((k & rmask) == 0) renormalise();
-        const int i = __shfl_sync(0xffffffffu, site_l, k);
-        const float thr = __shfl_sync(0xffffffffu, thr_l, k);
-        const uint32_t word = (i < 64) ? ((i < 32) ? sb[0] : sb[1]) : ((i < 96) ? sb[2] : sb[3]);
-        const bool neg = (word >> (i & 31)) & 1u;  // sigma_i = -1  =>  nu = +1
-        float2 t2[NP];
-        LM::load_row(sm.tau + (size_t)i * MP, lane, t2);
-        const float Rp = row_log2(t2, neg);
-        const float nu = neg ? 1.0f : -1.0f;
-        const float delta = fmaf(LN2, Rp - R, fmaf(nu, sm.a2[i], sm.lcrow[i]));
-        if (thr < delta) {
-          if (neg) {
-#pragma unroll
-            for (int q = 0; q < NP; ++q) {
-              const float2 cn = ffma2(t2[q], S2[q], C2[q]);
-              S2[q] = ffma2(t2[q], C2[q], S2[q]);
-              C2[q] = cn;
-            }
-          } else {
-#pragma unroll
-            for (int q = 0; q < NP; ++q) {
-              const float2 nt = neg2(t2[q]);
-              const float2 cn = ffma2(nt, S2[q], C2[q]);
-              S2[q] = ffma2(nt, C2[q], S2[q]);
-              C2[q] = cn;
-            }
-          }
-          const uint32_t bit = 1u << (i & 31);
-          sb[0] ^= (i < 32) ? bit : 0u;
-          sb[1] ^= (i >= 32 && i < 64) ? bit : 0u;
-          sb[2] ^= (i >= 64 && i < 96) ? bit : 0u;
-          sb[3] ^= (i >= 96) ? bit : 0u;
-          R = Rp;
-          logpsi += delta;
-          ++nacc;
+      const int nb = min(32, T_total - tt);
+      int k = 0;
+      while (k < nb) {
+        // a segment = proposals up to the end of the sweep / of this batch; rows are prefetched one proposal ahead
+        const int kend = k + min(nb - k, sweep_size - in_sweep);
+        in_sweep += kend - k;
+        // software pipeline: while proposal k runs, the G row, the threshold, the per-site constants and the spin of
+        // proposal k+1 are already in flight; the prefetched spin is patched if proposal k flips that very site
+        float2 gA[NP], gB[NP];
+        int siteA, siteB, thrA, thrB;
+        uint32_t ownA, ownB;
+        float2 rcA, rcB;
+#define NK_FETCH(G, SITE, THR, OWN, RC, KK)                                            \
+  {                                                                                    \
+    SITE = __shfl_sync(0xffffffffu, site_l, (KK));                                     \
+    const uint32_t roff = (uint32_t)SITE * (uint32_t)(MP * 4);                         \
+    LM::load_row(lane_row + roff, lane_tail + roff, G);                                \
+    RC = lds64(rc_s + 16u * SITE + 8u);                                                \
+    THR = __shfl_sync(0xffffffffu, thr_l, (KK));                                       \
+    OWN = __shfl_sync(0xffffffffu, c.mybits, SITE & 31);                               \
+  }
+#define NK_STEP(G, SITE, THR, OWN, RC, NSITE, NOWN)                                    \
+  {                                                                                    \
+    if (c.since >= renorm) renormalise();                                              \
+    const bool acc = ((OWN >> (SITE >> 5)) & 1u)                                       \
+                         ? propose<NP, true>(c, G, __float_as_int(RC.x), THR, SITE, lane_o)   \
+                         : propose<NP, false>(c, G, __float_as_int(RC.y), THR, SITE, lane_o); \
+    if (acc && ((SITE ^ NSITE) & 31) == 0) NOWN ^= 1u << (SITE >> 5);                  \
+  }
+        NK_FETCH(gA, siteA, thrA, ownA, rcA, k)
+        for (; k + 1 < kend; k += 2) {
+          NK_FETCH(gB, siteB, thrB, ownB, rcB, k + 1)
+          NK_STEP(gA, siteA, thrA, ownA, rcA, siteB, ownB)
+          NK_FETCH(gA, siteA, thrA, ownA, rcA, k + 2)  // beyond the batch: lanes hold site 0, a harmless prefetch
+          NK_STEP(gB, siteB, thrB, ownB, rcB, siteA, ownA)
         }
-        if (++in_sweep == p.sweep_size) {
+        if (k < kend) {
+          siteB = 32;  // no successor to patch
+          ownB = 0;
+          NK_STEP(gA, siteA, thrA, ownA, rcA, siteB, ownB)
+          ++k;
+        }
+#undef NK_STEP
+#undef NK_FETCH
+        if (in_sweep == sweep_size) {
           in_sweep = 0;
-          const int64_t sw = sweep_idx - p.n_discard;
+          const int sw = sweep_idx - p.n_discard;
           ++sweep_idx;
           if (sw >= 0) {
-            const int64_t o = chain * p.chain_length + sw;
-            if (p.samples_out != nullptr)
-              for (int n = lane; n < N; n += 32) p.samples_out[o * N + n] = ((sb[n >> 5] >> (n & 31)) & 1u) ? (int8_t)-1 : (int8_t)1;
-            if (p.logp_out != nullptr && lane == 0) reinterpret_cast<float *>(p.logp_out)[o] = pw * logpsi;
+            const size_t o = (size_t)chain * p.chain_length + sw;
+            if (p.samples_out != nullptr) {
+#pragma unroll
+              for (int b = 0; b < 4; ++b) {
+                const int idx = 32 * b + lane;
+                if (idx < N) p.samples_out[o * N + idx] = ((c.mybits >> b) & 1u) ? (int8_t)-1 : (int8_t)1;
+              }
+            }
+            if (p.logp_out != nullptr) {
+              const float lp = logpsi_now();
+              if (lane == 0) reinterpret_cast<float *>(p.logp_out)[o] = (float)p.machine_pow * lp;
+            }
             if (p.eloc_kind == 1) {
               // E_loc = J sum_<ij> s_i s_j - h sum_i exp(delta_i)
-              renormalise();
+              uint32_t sw4[4];
+#pragma unroll
+              for (int b = 0; b < 4; ++b) sw4[b] = __ballot_sync(0xffffffffu, (c.mybits >> b) & 1u);
               int zz = 0;
               for (int e = lane; e < E; e += 32) {
-                const int a = sm.edges[2 * e], b = sm.edges[2 * e + 1];
-                const uint32_t x = ((sb[a >> 5] >> (a & 31)) ^ (sb[b >> 5] >> (b & 31))) & 1u;
-                zz += 1 - 2 * (int)x;
+                const int a = edges[2 * e], bq = edges[2 * e + 1];
+                const uint32_t wa = (a < 64) ? ((a < 32) ? sw4[0] : sw4[1]) : ((a < 96) ? sw4[2] : sw4[3]);
+                const uint32_t wb = (bq < 64) ? ((bq < 32) ? sw4[0] : sw4[1]) : ((bq < 96) ? sw4[2] : sw4[3]);
+                zz += 1 - 2 * (int)(((wa >> (a & 31)) ^ (wb >> (bq & 31))) & 1u);
               }
               zz = __reduce_add_sync(0xffffffffu, zz);
               float off = 0.0f;
               if (hh != 0.0f) {
-                for (int s = 0; s < N; ++s) {
-                  const bool ng = (sb[s >> 5] >> (s & 31)) & 1u;
-                  float2 r2[NP];
-                  LM::load_row(sm.tau + (size_t)s * MP, lane, r2);
-                  const float Rs = row_log2(r2, ng);
-                  off += __expf(fmaf(LN2, Rs, fmaf(ng ? 1.0f : -1.0f, sm.a2[s], sm.lcrow[s])));
+                // accurate (float) normalisation log2 prod_j (A_j + B_j) for this sample
+                float nrm = 1.0f;
+#pragma unroll
+                for (int q = 0; q < NP; ++q) nrm *= (c.A2[q].x + c.B2[q].x) * (c.A2[q].y + c.B2[q].y);
+                const float Rf = warp_sum(lg2_fast(nrm));
+                // sites in groups of 16: 16 independent lane products (ILP), then a transposed butterfly that needs
+                // 16 shuffles for 16 sites instead of 80; lane l ends up with the total of site base + ((l >> 1) & 15)
+                float off_l = 0.0f;
+                const int myidx = (lane_o >> 1) & 15;
+#pragma unroll 1
+                for (int base = 0; base < N; base += 16) {
+                  const uint32_t word = sw4sel(sw4, base >> 5) >> (base & 16);
+                  float v[16];
+#pragma unroll
+                  for (int jj = 0; jj < 16; ++jj) {
+                    const int sidx = base + jj;
+                    v[jj] = 0.0f;
+                    if (sidx < N) {
+                      const uint32_t so = (uint32_t)sidx * (uint32_t)(MP * 4);
+                      float2 r2[NP];
+                      LM::load_row(lane_row + so, lane_tail + so, r2);
+                      const float Ps = ((word >> jj) & 1u) ? lane_product<NP>(c.B2, c.A2, r2) : lane_product<NP>(c.A2, c.B2, r2);
+                      v[jj] = lg2_fast(Ps);
+                    }
+                  }
+#pragma unroll
+                  for (int h = 8; h >= 1; h >>= 1) {
+                    const bool up = (lane_o & (2 * h)) != 0;
+#pragma unroll
+                    for (int jj = 0; jj < h; ++jj) {
+                      const float send = up ? v[jj] : v[jj + h];
+                      const float keep = up ? v[jj + h] : v[jj];
+                      v[jj] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * h);
+                    }
+                  }
+                  const float tot = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+                  const int mys = base + myidx;
+                  if (mys < N && (lane_o & 1) == 0) {
+                    const float2 rcs = lds64(rc_s + 16u * mys);
+                    const float cst = ((word >> myidx) & 1u) ? rcs.x + rcs.y : rcs.x - rcs.y;
+                    off_l += ex2_fast(tot - Rf + cst);
+                  }
                 }
+                off = warp_sum(off_l);
               }
               const float e_loc = JJ * (float)zz - hh * off;
               if (lane == 0) store_as<float>(p.eloc_out, o, e_loc, p.eloc_dtype);
@@ -353,10 +488,15 @@ __global__ void __launch_bounds__(FAST_THREADS, 1)
       }
     }
     // ---- write the chain state back
-    for (int n = lane; n < N; n += 32) p.sigma[chain * N + n] = ((sb[n >> 5] >> (n & 31)) & 1u) ? (int8_t)-1 : (int8_t)1;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int idx = 32 * b + lane;
+      if (idx < N) p.sigma[(size_t)chain * N + idx] = ((c.mybits >> b) & 1u) ? (int8_t)-1 : (int8_t)1;
+    }
+    const float lp = logpsi_now();
     if (lane == 0) {
-      reinterpret_cast<float *>(p.log_prob)[chain] = pw * logpsi;
-      p.n_accepted[chain] += nacc;
+      reinterpret_cast<float *>(p.log_prob)[chain] = (float)p.machine_pow * lp;
+      p.n_accepted[chain] += (int64_t)c.nacc;
     }
   }
 }
@@ -395,6 +535,7 @@ bool sweep_fast_supported(const SweepKernelArgs &a) {
   const int E = a.eloc_kind == 1 ? a.ising.n_edges : 0;
   if (fast_smem_bytes(a.rbm.N, fs.mp, E) > 227 * 1024) return false;
   if ((size_t)a.rbm.N * a.rbm.M * 4 >= (1u << 20)) return false;  // mbarrier tx-count range
+  if (a.B >= (1ll << 31) || (int64_t)(a.n_discard + a.chain_length) * a.sweep_size >= (1ll << 31)) return false;  // 32-bit counters
   return true;
 }
 
