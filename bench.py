@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py — E_loc samples/sec (1 sweep/sample), RBM alpha=4, 10x10 TFIM (BASELINE.json metric), on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dtype float32|float64]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one pass of the hot path over one batch: `vs.reset(); vs.expect(H)`, i.e. for every chain
+`chain_length` x (one sweep of N Metropolis proposals + the local energy of the resulting sample) + the MC
+statistics (only scalars cross GPUs).  Workload: N=100, M=400, h=3, J=1, W,b,a ~ N(0, 0.01^2)
+from default_rng(1234), 2^16 chains per GPU (weak scaling: chains are independent, no data-path collective),
+chain_length 16, 5 untimed burn-in sweeps.
+
+Printed JSON (one line, rank 0):
+  value      whole-job samples/s with inputs resident in HBM, CUDA events around the K steps, max over ranks
+  e2e        the same metric through the host-buffer C ABI (nk_ctx_step_host): parameters H2D from pinned memory
+             and E_loc + statistics D2H inside the timed region, every step
+  roofline   dominant kernel (fused sweep + E_loc): algorithmic shared-memory operand bytes / kernel time vs the
+             shared-memory read bandwidth measured in this run (nk_microbench)
+  cpu_baseline  the reference *algorithm* (oracle/reference_algorithm.py, kind "port") on this box's host cores
+"""
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+L_SIDE, ALPHA, H_FIELD, J_COUP = 10, 4, 3.0, 1.0
+N_SITES, N_HIDDEN = L_SIDE * L_SIDE, ALPHA * L_SIDE * L_SIDE
+CHAINS_PER_GPU = 1 << 16
+CHAIN_LENGTH = 16
+WEIGHT_SEED, SAMPLER_SEED = 1234, 15324
+METRIC = "E_loc samples/sec (1 sweep/sample), RBM a=4 10x10 TFIM"
+CPU_SAMPLE_CHAINS = 1024
+
+
+def workload_name(dtype):
+    return (f"TFIM 10x10 pbc h=3 J=1, RBM alpha=4 (N=100, M=400) {dtype}, MetropolisLocal, {CHAINS_PER_GPU} chains/GPU x "
+            f"chain_length {CHAIN_LENGTH} (sweep_size=N), fused E_loc + statistics per step")
+
+
+def bytes_per_sample(esz):
+    """Algorithmic on-chip operand bytes per (sweep + E_loc) sample: N proposals + N flips, one W row of M elements each
+    (SURVEY.md §8d): 2 * N * M * sizeof(T)."""
+    return 2 * N_SITES * N_HIDDEN * esz
+
+
+# ------------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-i",
+                                          str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+                power.append(float(r[3]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------- reference arm
+def edges_np():
+    from oracle import graph as ograph
+
+    return ograph.hypercube_edges(L_SIDE, 2)[0]
+
+
+def run_cpu(dtype, steps, warmup):
+    """The reference algorithm on the host cores, on a bounded sample of the workload (see cpu_baseline.sample)."""
+    from oracle import reference_algorithm as ra
+
+    val, ms, threads = ra.time_vmc_steps(N_SITES, N_HIDDEN, CPU_SAMPLE_CHAINS, 1, edges_np(), H_FIELD, J_COUP, np.dtype(dtype).type,
+                                         steps=steps, warmup=warmup, seed=SAMPLER_SEED)
+    sample = (f"{CPU_SAMPLE_CHAINS} chains x 1 (sweep + E_loc) per step, {steps} timed steps after {warmup} warm-up; same "
+              "N, M, h, J, parameters and algorithmic structure as the GPU workload; throughput is linear in the number "
+              "of chains once the GEMMs saturate the cores")
+    return val, ms, {"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample,
+                     "what": "reference algorithm (full forward pass per proposal, materialised connected states), torch CPU "
+                             "kernels on all host threads; NetKet's jax[cpu] path itself cannot run: jax is not installed"}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 3))
+    val, ms, cpu = run_cpu(args.dtype, steps, warmup)
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus, "steps": steps,
+           "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32" if args.dtype == "float32" else "f64", "data": "synthetic",
+           "config": {"workload": workload_name(args.dtype), "parallelism": "host CPU threads", "note": cpu["sample"]},
+           "cpu_baseline": cpu, "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------- our arm
+def build_state(nk, torch, dtype, device, chains):
+    g = nk.graph.Hypercube(L_SIDE, 2, pbc=True)
+    hi = nk.hilbert.Spin(0.5, g.n_nodes)
+    ha = nk.operator.Ising(hi, g, h=H_FIELD, J=J_COUP)
+    model = nk.models.RBM(alpha=ALPHA, param_dtype=dtype)
+    var = model.init(WEIGHT_SEED, N_SITES, device=device)  # W, b, a ~ N(0, 0.01^2) from numpy default_rng(1234)
+    Wt, bt, at = nk.models.RBM.unpack(var)
+    sa = nk.sampler.MetropolisLocal(hi, n_chains_per_rank=chains)
+    vs = nk.vqs.MCState(sa, model, variables=var, n_samples_per_rank=chains * CHAIN_LENGTH, n_discard_per_chain=0,
+                        sampler_seed=SAMPLER_SEED)
+    return g, hi, ha, vs, (Wt.cpu().numpy(), bt.cpu().numpy(), at.cpu().numpy())
+
+
+def timed_steps(torch, dist, ws, fn, steps, warmup):
+    """W warm-up + K timed steps, CUDA events on the current stream, barrier + synchronize on both sides, max over ranks."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if ws > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if ws > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if ws > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def measure(nk, torch, dist, rank, ws, device, dtype, steps, warmup):
+    from netket_b200 import _lib
+
+    L = _lib.lib()
+    esz = 4 if dtype == "float32" else 8
+    g, hi, ha, vs, (W, b, a) = build_state(nk, torch, dtype, device, CHAINS_PER_GPU)
+    # burn-in: 5 sweeps, untimed (netket/vqs/mc/mc_state/state.py:466-468)
+    vs.sample(chain_length=CHAIN_LENGTH, n_discard_per_chain=5)
+    result = {}
+
+    def step():
+        vs.reset()
+        result["stats"] = vs.expect(ha)
+
+    launches0 = L.nk_launch_count()
+    ms = timed_steps(torch, dist, ws, step, steps, warmup)
+    launches = (L.nk_launch_count() - launches0) // (steps + warmup)  # our kernels per step
+    samples_per_step = CHAINS_PER_GPU * CHAIN_LENGTH * ws
+    value = samples_per_step * steps / (ms * 1e-3)
+
+    # ---- dominant kernel alone: the fused sweep + E_loc launch (nk_sweep minus the theta kernel that precedes it)
+    sa = vs.sampler
+    st0 = vs.sampler_state
+
+    def sweep_only():
+        sa._launch(vs.model, vs.variables, st0, CHAIN_LENGTH, operator=ha, want_samples=True)
+
+    ms_sweep_call = timed_steps(torch, dist, 1, sweep_only, max(3, steps // 2), 2) / max(3, steps // 2)
+    rbm = nk.models.RBM.c_struct(vs.variables)
+    theta = torch.empty((CHAINS_PER_GPU, N_HIDDEN), dtype=vs.variables["params"]["Dense"]["kernel"].dtype, device=device)
+    scratch = torch.empty(int(L.nk_theta_gemm_workspace_bytes(C.byref(rbm), CHAINS_PER_GPU)), dtype=torch.uint8, device=device)
+
+    def theta_only():
+        _lib.check(L.nk_theta_gemm(_lib.stream_ptr(device), C.byref(rbm), _lib.ptr(st0.σ), CHAINS_PER_GPU, _lib.ptr(theta),
+                                   _lib.ptr(scratch)))
+
+    ms_theta = timed_steps(torch, dist, 1, theta_only, 5, 2) / 5 if dtype == "float32" else 0.0
+    ms_kernel = ms_sweep_call - ms_theta
+    alg_bytes = CHAINS_PER_GPU * CHAIN_LENGTH * bytes_per_sample(esz)
+    achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
+    res = C.c_double()
+    which, bound = (0, "smem") if dtype == "float32" else (1, "l2")
+    _lib.check(L.nk_microbench(which, C.byref(res)))
+    peak = float(res.value)
+    roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "sweep_fast_kernel<3,1> (fused sweep + E_loc)" if dtype == "float32" else "sweep_generic_kernel<double>",
+                "kernel_ms": ms_kernel, "theta_kernel_ms": ms_theta,
+                "algorithmic_bytes_per_sample": bytes_per_sample(esz),
+                "peak_source": f"measured in this run by nk_microbench({which}) ({'LDS.128 shared-memory' if which == 0 else 'L2'} read "
+                               "bandwidth, all SMs); MEASURED_PEAKS.json holds no on-chip figure (its HBM copy number does not bound "
+                               "this path: HBM traffic is ~120 B/sample)",
+                "method": "CUDA events on the launching stream around nk_sweep, minus the separately timed theta kernel"}
+    return {"value": value, "ms_per_step": ms / steps, "launches": launches, "roofline": roofline, "stats": result["stats"],
+            "acceptance": vs.sampler_state.acceptance, "params": (W, b, a)}
+
+
+def measure_e2e(nk, torch, dist, rank, ws, device, dtype, steps, warmup, params):
+    """Host-buffer C ABI: parameters from pinned host memory every step, E_loc + statistics back to the host."""
+    from netket_b200 import _lib
+
+    L = _lib.lib()
+    W, b, a = params
+    esz = W.dtype.itemsize
+    ctx = C.c_void_p()
+    e = np.ascontiguousarray(np.asarray(nk.graph.Hypercube(L_SIDE, 2, pbc=True).edges()), dtype=np.int32)
+    _lib.check(L.nk_ctx_create(C.byref(ctx), device.index, N_SITES, N_HIDDEN, _lib.dtype_code(W.dtype), CHAINS_PER_GPU, CHAIN_LENGTH,
+                               e.ctypes.data_as(C.c_void_p), e.shape[0], H_FIELD, J_COUP, SAMPLER_SEED, rank * CHAINS_PER_GPU))
+    pin = lambda x: torch.from_numpy(x).pin_memory()  # noqa: E731
+    Wp, bp, ap = pin(W), pin(b), pin(a)
+    eloc = torch.empty((CHAINS_PER_GPU, CHAIN_LENGTH), dtype=Wp.dtype).pin_memory()
+    stats = (C.c_double * 6)()
+
+    def step(n_discard=0):
+        _lib.check(L.nk_ctx_step_host(ctx, Wp.data_ptr(), bp.data_ptr(), ap.data_ptr(), n_discard, eloc.data_ptr(), stats))
+
+    step(5)
+    for _ in range(warmup):
+        step()
+    if ws > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    tic = time.perf_counter()
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - tic
+    if ws > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    L.nk_ctx_destroy(ctx)
+    return {"value": CHAINS_PER_GPU * CHAIN_LENGTH * ws * steps / dt, "unit": "samples/s",
+            "h2d_bytes_per_step": int((W.size + b.size + a.size) * esz),
+            "d2h_bytes_per_step": int(CHAINS_PER_GPU * CHAIN_LENGTH * esz + 8 * 8 * 2 + 8),
+            "api": "nk_ctx_step_host (include/nkb200.h): W,b,a from pinned host memory; E_loc[chains, chain_length], the 5 "
+                   "statistics and the acceptance back to host memory; synchronous",
+            "mean_energy": stats[0], "acceptance": stats[5]}
+
+
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: netket_b200 has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if ws > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    import __graft_entry__
+
+    if rank == 0:
+        __graft_entry__.build()
+    if ws > 1:
+        dist.barrier()
+    import netket_b200 as nk
+
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    main = measure(nk, torch, dist, rank, ws, device, args.dtype, args.steps, args.warmup)
+    e2e = measure_e2e(nk, torch, dist, rank, ws, device, args.dtype, args.steps, args.warmup, main["params"])
+    clk = clocks.stop() if rank == 0 else None
+    other = "float64" if args.dtype == "float32" else "float32"
+    extra = None
+    if not args.no_second_dtype:
+        k2 = max(2, args.steps // 5) if other == "float64" else args.steps
+        m2 = measure(nk, torch, dist, rank, ws, device, other, k2, 1)
+        extra = {"dtype": other, "value": m2["value"], "unit": "samples/s", "steps": k2, "ms_per_step": m2["ms_per_step"],
+                 "roofline": m2["roofline"], "mean_energy": m2["stats"].mean}
+    cpu = None
+    if rank == 0 and ws == 1 and not args.no_cpu:
+        _, _, cpu = run_cpu(args.dtype, 12, 1)
+    if rank == 0:
+        st = main["stats"]
+        out = {"metric": METRIC, "value": main["value"], "unit": "samples/s", "n_gpus": ws, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f32" if args.dtype == "float32" else "f64", "data": "synthetic",
+               "config": {"workload": workload_name(args.dtype), "parallelism": f"chains sharded over {ws} GPU(s), one process per GPU; "
+                          "only the statistics scalars are all-reduced (NCCL)",
+                          "l2": "no explicit L2 flush: the path is bound by shared-memory operand reads (W is staged once per CTA); "
+                                "per step it streams 105 MB of theta scratch and 105 MB of samples through HBM, more than the 126 MB L2",
+                          "weights": "W,b,a ~ N(0, 0.01^2), numpy default_rng(1234); sampler seed 15324; 5 burn-in sweeps untimed"},
+               "e2e": e2e, "gpu_launches": int(main["launches"] * args.steps), "gpu_launches_per_step": int(main["launches"]),
+               "roofline": main["roofline"], "clocks": clk,
+               "result": {"energy_mean": st.mean, "energy_sigma": st.error_of_mean, "variance": st.variance, "R_hat": st.R_hat,
+                          "tau_corr": st.tau_corr, "acceptance": main["acceptance"]}}
+        if extra is not None:
+            out["second_dtype"] = extra
+        if cpu is not None:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out))
+    if ws > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-second-dtype", action="store_true", help="skip the shorter run in the other precision")
+    a = ap.parse_args()
+    if a.warmup < 3 and a.impl == "ours":
+        a.warmup = 3
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_ours(a)

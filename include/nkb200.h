@@ -127,6 +127,8 @@ typedef struct nk_sweep_t {
 
 const char *nk_last_error(void);
 int nk_version(void);
+/* number of CUDA kernels this library has launched in this process (a statistics counter; bench.py's gpu_launches) */
+long long nk_launch_count(void);
 
 /* RBM.apply: logpsi[B] = sum_j lncosh(sum_i sigma_i W_ij + b_j) + sum_i a_i sigma_i.
  * Replaces netket/models/rbm.py:57-81 + netket/nn/activation.py:78-84 (seam S5).

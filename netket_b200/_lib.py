@@ -61,6 +61,7 @@ class nk_sweep_t(C.Structure):
 SYMBOLS = {
     "nk_last_error": (C.c_char_p, []),
     "nk_version": (C.c_int, []),
+    "nk_launch_count": (C.c_longlong, []),
     "nk_rbm_logpsi": (C.c_int, [C.c_void_p, C.POINTER(nk_rbm_t), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "nk_theta_gemm_workspace_bytes": (C.c_int64, [C.POINTER(nk_rbm_t), C.c_int64]),
     "nk_theta_gemm": (C.c_int, [C.c_void_p, C.POINTER(nk_rbm_t), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),

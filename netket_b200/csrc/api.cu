@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 #include <vector>
 
@@ -17,6 +18,9 @@ void set_error(const char *fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int num_sms() {
   static std::mutex mu;
@@ -83,6 +87,7 @@ extern "C" {
 
 const char *nk_last_error(void) { return g_err; }
 int nk_version(void) { return NK_VERSION; }
+long long nk_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int nk_rbm_logpsi(void *stream, const nk_rbm_t *rbm, const int8_t *sigma, int64_t B, void *logpsi_out, void *theta_out) {
   int rc = check_rbm(rbm, "nk_rbm_logpsi");
@@ -286,6 +291,7 @@ struct nk_ctx {
   double *partials_host;  // pinned
   int64_t *nacc_host;     // pinned, 1
   int64_t *nacc_sum;      // device, 1
+  void *workspace;        // nk_sweep_workspace_bytes (theta scratch + hand-over flag)
   nk_ising_t ising;
   uint64_t seed, t, chain_offset;
 };
@@ -329,6 +335,15 @@ int nk_ctx_create(nk_ctx **out, int32_t device, int32_t N, int32_t M, int32_t dt
   NK_CUDA_OK(cudaMalloc(&c->eloc, (size_t)n_chains * chain_length * c->esz));
   NK_CUDA_OK(cudaMalloc((void **)&c->partials, sizeof(double) * NK_STATS_NPARTIAL));
   NK_CUDA_OK(cudaMalloc((void **)&c->nacc_sum, 8));
+  {
+    nk_rbm_t shape{};
+    shape.W = c->W;
+    shape.N = N;
+    shape.M = M;
+    shape.dtype = dtype;
+    const int64_t wsb = nk_sweep_workspace_bytes(&shape, n_chains);
+    if (wsb > 0) NK_CUDA_OK(cudaMalloc(&c->workspace, (size_t)wsb));
+  }
   NK_CUDA_OK(cudaMallocHost((void **)&c->partials_host, sizeof(double) * NK_STATS_NPARTIAL));
   NK_CUDA_OK(cudaMallocHost((void **)&c->nacc_host, 8));
   if (n_edges > 0) NK_CUDA_OK(cudaMemcpyAsync(c->edges, edges_host, (size_t)n_edges * 8, cudaMemcpyHostToDevice, c->stream));
@@ -357,6 +372,7 @@ void nk_ctx_destroy(nk_ctx *c) {
   cudaFree(c->eloc);
   cudaFree(c->partials);
   cudaFree(c->nacc_sum);
+  cudaFree(c->workspace);
   cudaFreeHost(c->partials_host);
   cudaFreeHost(c->nacc_host);
   cudaStreamDestroy(c->stream);
@@ -384,6 +400,7 @@ int nk_ctx_step_host(nk_ctx *c, const void *W_host, const void *b_host, const vo
   ch.sigma = c->sigma;
   ch.log_prob = c->log_prob;
   ch.n_accepted = c->n_accepted;
+  ch.workspace = c->workspace;
   ch.B = c->B;
   ch.seed = c->seed;
   ch.t = c->t;

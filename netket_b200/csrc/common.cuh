@@ -31,6 +31,7 @@ void set_error(const char *fmt, ...);
 
 #define NK_LAUNCH_OK()                                                                     \
   do {                                                                                     \
+    nk::count_launch();                                                                    \
     cudaError_t _e = cudaGetLastError();                                                   \
     if (_e != cudaSuccess) {                                                               \
       nk::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
@@ -39,6 +40,7 @@ void set_error(const char *fmt, ...);
   } while (0)
 
 int num_sms();  // SM count of the current device (cached per device)
+void count_launch();  // statistics only: number of kernels this library has launched (nk_launch_count)
 
 // ------------------------------------------------------------------ math in the working precision
 template <typename T>
