@@ -67,14 +67,16 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
                : "memory");
 }
 
+#ifndef NK_FAST_PREFETCH
+#define NK_FAST_PREFETCH 0
+#endif
 #ifndef NK_FAST_WARPS
-#define NK_FAST_WARPS 20
+#define NK_FAST_WARPS 28
 #endif
 constexpr int FAST_WARPS = NK_FAST_WARPS;
 constexpr int FAST_THREADS = FAST_WARPS * 32;
 constexpr float EXP_RANGE = 120.0f;  // log2 headroom allowed for a lane product
 constexpr float FX_SCALE = 524288.0f;            // 2^19: fixed-point scale of per-lane log2 partials (REDUX add)
-constexpr float FX_INV = 1.0f / 524288.0f;
 
 // ---- explicit shared-space accesses (32-bit shared addresses kept in registers; no generic-address arithmetic)
 __device__ __forceinline__ float4 lds128(uint32_t a) {
@@ -388,6 +390,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1)
                          : propose<NP, false>(c, G, __float_as_int(RC.y), THR, SITE, lane_o); \
     if (acc && ((SITE ^ NSITE) & 31) == 0) NOWN ^= 1u << (SITE >> 5);                  \
   }
+#if NK_FAST_PREFETCH
         NK_FETCH(gA, siteA, thrA, ownA, rcA, k)
         for (; k + 1 < kend; k += 2) {
           NK_FETCH(gB, siteB, thrB, ownB, rcB, k + 1)
@@ -401,6 +404,16 @@ __global__ void __launch_bounds__(FAST_THREADS, 1)
           NK_STEP(gA, siteA, thrA, ownA, rcA, siteB, ownB)
           ++k;
         }
+#else
+        // measured on B200: resident warps matter more than row prefetch (28 warps x 72 registers beats 20 x 96)
+        (void)gB; (void)thrB; (void)rcB;
+        for (; k < kend; ++k) {
+          NK_FETCH(gA, siteA, thrA, ownA, rcA, k)
+          siteB = 32;
+          ownB = 0;
+          NK_STEP(gA, siteA, thrA, ownA, rcA, siteB, ownB)
+        }
+#endif
 #undef NK_STEP
 #undef NK_FETCH
         if (in_sweep == sweep_size) {
