@@ -117,13 +117,13 @@ int nk_random_state(void *stream, int8_t *sigma, int64_t B, int32_t N, int32_t n
   return random_state((cudaStream_t)stream, sigma, B, N, n_down, seed, chain_offset);
 }
 
-// workspace layout of the fast path: [theta: B*M floats | pad to 256] [flags: 256 B] [scratch: B floats]
+// workspace layout of the fast path: [theta: B*M floats | pad to 256] [flags: 256 B] [theta-GEMM workspace]
 static inline size_t ws_theta_bytes(const nk_rbm_t *rbm, int64_t B) { return (((size_t)B * rbm->M * 4) + 255) & ~(size_t)255; }
 
 int64_t nk_sweep_workspace_bytes(const nk_rbm_t *rbm, int64_t B) {
   if (check_rbm(rbm, "nk_sweep_workspace_bytes") || B < 0) return -1;
   if (rbm->dtype != NK_F32) return 0;  // generic path: theta lives in shared memory for the whole call
-  return (int64_t)(ws_theta_bytes(rbm, B) + 256 + (((size_t)B * 4 + 255) & ~(size_t)255));
+  return (int64_t)(ws_theta_bytes(rbm, B) + 256 + (size_t)theta_gemm_workspace_bytes(*rbm, B));
 }
 
 int nk_sweep(void *stream, const nk_rbm_t *rbm, nk_chains_t *ch, const nk_sweep_t *a) {

@@ -1,10 +1,269 @@
-// theta = sigma W + b.  Interim CUDA-core version (the tensor-core kernel replaces this file's body).
+// theta[B, M] = sigma[B, N] W[N, M] + b  — the only dense contraction on the path
+// (nn.Dense of netket/models/rbm.py:59-67, evaluated at `_reset`, netket/sampler/metropolis.py:399-403).
+//
+// fp32: 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM).  The product is made EXACT in fp32 terms by
+// splitting W into three bf16 parts, W = W1 + W2 + W3 (8+8+8 mantissa bits), while sigma in {+1,-1} is exact in bf16:
+//     theta = sigma W1 + sigma W2 + sigma W3          (fp32 accumulation in TMEM, 3 x K/16 MMAs per tile)
+// so the result differs from an fp32 FMA chain only by summation order.
+//   * a prep kernel writes the three bf16 parts of W^T as ready-made shared-memory images (K-major, no-swizzle
+//     core-matrix layout: 8 rows x 16 bytes per core matrix);
+//   * each CTA (128 threads, persistent) bulk-copies its N-tile image once (cp.async.bulk + mbarrier), then per block of
+//     128 configurations: threads convert sigma (int8) to bf16 straight into the A tile, one thread issues the MMAs
+//     (UMMA 128 x NT x 16, cta_group::1), tcgen05.commit signals an mbarrier, and the four warps read their TMEM lane
+//     quarter with tcgen05.ld, add the bias and store theta.
+// fp64 (and shapes outside the tensor-core kernel's limits): the CUDA-core kernel rbm_logpsi_kernel.
 #include "kernels.cuh"
 
 namespace nk {
+
 int rbm_logpsi(cudaStream_t stream, const nk_rbm_t &rbm, const int8_t *sigma, int64_t B, void *out, void *theta_out);
 
-int64_t theta_gemm_workspace_bytes(const nk_rbm_t &rbm, int64_t B) { return B * (rbm.dtype == NK_F32 ? 4 : 8); }
+// ---------------------------------------------------------------------------------------------- geometry
+struct TcGeom {
+  int kpad;     // N rounded up to a multiple of 16
+  int nt;       // number of N-tiles (1 or 2)
+  int NT;       // tile width (multiple of 16, <= 256)
+  int sbo;      // bytes between 8-row groups = (kpad / 8) * 128
+  size_t part_bytes;   // one bf16 part of one N-tile image
+  size_t img_bytes;    // 3 parts
+  size_t a_bytes;      // A tile (128 rows)
+  size_t smem_bytes;
+  int tmem_cols;
+};
+
+static bool tc_geometry(const nk_rbm_t &rbm, TcGeom *g) {
+  if (rbm.dtype != NK_F32 || rbm.N > 128 || rbm.M > 512 || rbm.M < 16) return false;
+  g->kpad = (rbm.N + 15) & ~15;
+  g->nt = rbm.M <= 256 ? 1 : 2;
+  const int per = (rbm.M + g->nt - 1) / g->nt;
+  g->NT = (per + 15) & ~15;
+  g->sbo = (g->kpad / 8) * 128;
+  g->part_bytes = (size_t)(g->NT / 8) * g->sbo;
+  g->img_bytes = 3 * g->part_bytes;
+  g->a_bytes = (size_t)16 * g->sbo;
+  g->smem_bytes = g->img_bytes + g->a_bytes + 64;
+  g->tmem_cols = g->NT <= 32 ? 32 : (g->NT <= 64 ? 64 : (g->NT <= 128 ? 128 : 256));
+  return g->smem_bytes <= 220 * 1024 && g->img_bytes < (1u << 20);
+}
+
+// ---------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  // tcgen05 shared-memory matrix descriptor, SWIZZLE_NONE: [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version = 1
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+__device__ __forceinline__ uint16_t f32_to_bf16_rn(float x) {
+  uint32_t u = __float_as_uint(x);
+  u += 0x7FFFu + ((u >> 16) & 1u);  // round to nearest even (inputs are finite)
+  return (uint16_t)(u >> 16);
+}
+__device__ __forceinline__ float bf16_to_f32(uint16_t h) { return __uint_as_float((uint32_t)h << 16); }
+
+// ---------------------------------------------------------------------------------------------- prep: W -> 3 bf16 images
+// image[tile][part][(n / 8) * sbo + (k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2],  n = column inside the tile, k = site
+__global__ void theta_prep_kernel(const float *__restrict__ W, int N, int M, int kpad, int nt, int NT, int sbo, uint16_t *__restrict__ img) {
+  const int total = nt * NT * kpad;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int k = idx % kpad;
+    const int ncol = (idx / kpad) % NT;
+    const int tile = idx / (kpad * NT);
+    const int j = tile * NT + ncol;
+    const float w = (k < N && j < M) ? W[(size_t)k * M + j] : 0.0f;
+    const uint16_t h1 = f32_to_bf16_rn(w);
+    const float r1 = w - bf16_to_f32(h1);
+    const uint16_t h2 = f32_to_bf16_rn(r1);
+    const float r2 = r1 - bf16_to_f32(h2);
+    const uint16_t h3 = f32_to_bf16_rn(r2);
+    const size_t part_elems = (size_t)(NT / 8) * sbo / 2;
+    const size_t off = (size_t)(ncol / 8) * (sbo / 2) + (size_t)(k / 8) * 64 + (size_t)(ncol % 8) * 8 + (k % 8);
+    uint16_t *base = img + (size_t)tile * 3 * part_elems;
+    base[off] = h1;
+    base[part_elems + off] = h2;
+    base[2 * part_elems + off] = h3;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- GEMM
+struct TcArgs {
+  const int8_t *sigma;
+  const uint16_t *img;
+  const float *bias;
+  float *theta;
+  int64_t B;
+  int N, M, kpad, nt, NT, sbo, tmem_cols;
+  uint32_t part_bytes, img_bytes;
+};
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
+__global__ void __launch_bounds__(128, 1) theta_tc_kernel(const __grid_constant__ TcArgs p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char *b_img = smem;                          // 3 parts, K-major core-matrix layout
+  unsigned char *a_tile = smem + p.img_bytes;           // 128 x kpad bf16, same layout
+  uint64_t *bars = reinterpret_cast<uint64_t *>(a_tile + (size_t)16 * p.sbo);
+  uint64_t *bar_load = bars, *bar_mma = bars + 1;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tile = blockIdx.x % p.nt;
+  const int n0 = tile * p.NT;
+
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(bar_load)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(bar_mma)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (tid == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar_load)), "r"(p.img_bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(b_img)),
+                 "l"(reinterpret_cast<const unsigned char *>(p.img) + (size_t)tile * p.img_bytes), "r"(p.img_bytes), "r"(s32(bar_load))
+                 : "memory");
+  }
+  {  // wait for the W image
+    uint32_t done = 0;
+    do {
+      asm volatile("{\n.reg .pred q;\nmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\nselp.u32 %0, 1, 0, q;\n}\n"
+                   : "=r"(done)
+                   : "r"(s32(bar_load)), "r"(0u)
+                   : "memory");
+    } while (!done);
+  }
+
+  // instruction descriptor, kind::f16: D = F32 (bit 4), A = B = BF16 (bits 7, 10), both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const int64_t n_blocks = (p.B + 127) / 128;
+  const int ctas_per_tile = gridDim.x / p.nt;
+  uint32_t mma_phase = 0;
+
+  for (int64_t rb = blockIdx.x / p.nt; rb < n_blocks; rb += ctas_per_tile) {
+    // ---- A tile: row = tid of this block, sigma int8 -> bf16 (+1 = 0x3F80, -1 = 0xBF80), zero beyond N / beyond B
+    {
+      const int64_t row = rb * 128 + tid;
+      const int8_t *src = p.sigma + row * p.N;
+      unsigned char *dst = a_tile + (size_t)(tid >> 3) * p.sbo + (size_t)(tid & 7) * 16;
+      for (int c = 0; c < p.kpad / 8; ++c) {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if (row < p.B) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int k = 8 * c + e;
+            const uint32_t h = (k < p.N) ? (src[k] < 0 ? 0xBF80u : 0x3F80u) : 0u;
+            w[e >> 1] |= h << (16 * (e & 1));
+          }
+        }
+        *reinterpret_cast<uint4 *>(dst + (size_t)c * 128) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core (async proxy)
+    __syncthreads();
+    // ---- MMAs: 3 bf16 parts x (kpad / 16) K-steps into one accumulator
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a_s = s32(a_tile), b_s = s32(b_img);
+      int first = 1;
+      for (int part = 0; part < 3; ++part) {
+        for (int ks = 0; ks < p.kpad / 16; ++ks) {
+          const uint64_t adesc = make_smem_desc(a_s + ks * 256, 128, (uint32_t)p.sbo);
+          const uint64_t bdesc = make_smem_desc(b_s + part * p.part_bytes + ks * 256, 128, (uint32_t)p.sbo);
+          const uint32_t acc = first ? 0u : 1u;
+          asm volatile(
+              "{\n.reg .pred q;\nsetp.ne.b32 q, %4, 0;\n"
+              "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, q;\n}\n" ::"r"(tmem_base),
+              "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+              : "memory");
+          first = 0;
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar_mma)) : "memory");
+    }
+    {  // all threads wait for the accumulator
+      uint32_t done = 0;
+      do {
+        asm volatile("{\n.reg .pred q;\nmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\nselp.u32 %0, 1, 0, q;\n}\n"
+                     : "=r"(done)
+                     : "r"(s32(bar_mma)), "r"(mma_phase)
+                     : "memory");
+      } while (!done);
+      mma_phase ^= 1u;
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ---- epilogue: warp w owns TMEM lanes 32w..32w+31 = rows 32w..32w+31 of the block
+    {
+      const int64_t row = rb * 128 + tid;
+      float *out = p.theta + row * p.M;
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+      for (int c0 = 0; c0 < p.NT; c0 += 32) {
+        uint32_t r[32];
+        const int width = min(32, p.NT - c0);
+        if (width == 32)
+          tmem_ld32(lane_addr + c0, r);
+        else
+          tmem_ld16(lane_addr + c0, r);  // NT is a multiple of 16
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row < p.B) {
+          if (width == 32) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const int j = n0 + c0 + e;
+              if (j < p.M) out[j] = __uint_as_float(r[e]) + (p.bias != nullptr ? p.bias[j] : 0.0f);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const int j = n0 + c0 + e;
+              if (j < p.M) out[j] = __uint_as_float(r[e]) + (p.bias != nullptr ? p.bias[j] : 0.0f);
+            }
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();  // TMEM and the A tile are free again
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host
+int64_t theta_gemm_workspace_bytes(const nk_rbm_t &rbm, int64_t B) {
+  TcGeom g;
+  if (tc_geometry(rbm, &g)) return (int64_t)(((size_t)g.nt * g.img_bytes + 255) & ~(size_t)255);
+  return (int64_t)((((size_t)B * (rbm.dtype == NK_F32 ? 4 : 8)) + 255) & ~(size_t)255);  // CUDA-core kernel: logpsi scratch
+}
 
 int theta_gemm(cudaStream_t stream, const nk_rbm_t &rbm, const int8_t *sigma, int64_t B, void *theta_out, void *workspace) {
   if (B == 0) return NK_OK;
@@ -12,6 +271,37 @@ int theta_gemm(cudaStream_t stream, const nk_rbm_t &rbm, const int8_t *sigma, in
     set_error("nk_theta_gemm: workspace is NULL");
     return NK_EINVAL;
   }
-  return rbm_logpsi(stream, rbm, sigma, B, workspace, theta_out);
+  TcGeom g;
+  if (!tc_geometry(rbm, &g)) return rbm_logpsi(stream, rbm, sigma, B, workspace, theta_out);
+  uint16_t *img = reinterpret_cast<uint16_t *>(workspace);
+  {
+    const int total = g.nt * g.NT * g.kpad;
+    theta_prep_kernel<<<(total + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const float *>(rbm.W), rbm.N, rbm.M, g.kpad, g.nt, g.NT,
+                                                               g.sbo, img);
+    NK_LAUNCH_OK();
+  }
+  TcArgs a{};
+  a.sigma = sigma;
+  a.img = img;
+  a.bias = reinterpret_cast<const float *>(rbm.b);
+  a.theta = reinterpret_cast<float *>(theta_out);
+  a.B = B;
+  a.N = rbm.N;
+  a.M = rbm.M;
+  a.kpad = g.kpad;
+  a.nt = g.nt;
+  a.NT = g.NT;
+  a.sbo = g.sbo;
+  a.tmem_cols = g.tmem_cols;
+  a.part_bytes = (uint32_t)g.part_bytes;
+  a.img_bytes = (uint32_t)g.img_bytes;
+  NK_CUDA_OK(cudaFuncSetAttribute(theta_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+  const int64_t n_blocks = (B + 127) / 128;
+  int64_t ctas = (int64_t)(num_sms() / g.nt) * g.nt;
+  if (ctas > n_blocks * g.nt) ctas = n_blocks * g.nt;
+  theta_tc_kernel<<<(int)ctas, 128, g.smem_bytes, stream>>>(a);
+  NK_LAUNCH_OK();
+  return NK_OK;
 }
+
 }  // namespace nk

@@ -26,7 +26,7 @@ def states_to_local_indices(x):
 
 def local_indices_to_states(idx, dtype=np.int8):
     """local index -> sigma.  static_range.py:172-192."""
-    return (START + STEP * np.asarray(idx).astype(np.int64)).astype(dtype)
+    return np.ascontiguousarray((START + STEP * np.asarray(idx).astype(np.int64)).astype(dtype))
 
 
 def n_excitations(N, total_sz):
@@ -83,7 +83,7 @@ def random_state(seed, n_chains, N, total_sz=None, chain_offset=0):
         words = words.reshape(n_chains, n_blocks * 4)
         site = np.arange(N)
         bits = (words[:, site // 32] >> (site % 32).astype(np.uint32)) & np.uint32(1)
-        return local_indices_to_states(bits)
+        return np.ascontiguousarray(local_indices_to_states(bits))
     n_exc = n_excitations(N, total_sz)
     if not (0 <= n_exc <= N):
         raise ValueError("total_sz incompatible with N")
@@ -98,4 +98,4 @@ def random_state(seed, n_chains, N, total_sz=None, chain_offset=0):
         tmp = idx[rows, i].copy()
         idx[rows, i] = idx[rows, j]
         idx[rows, j] = tmp
-    return local_indices_to_states(idx)
+    return np.ascontiguousarray(local_indices_to_states(idx))

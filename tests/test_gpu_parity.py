@@ -469,3 +469,29 @@ def test_fast_sampler_chi_square(cuda, std):
     pv = sstats.chisquare(counts, p * counts.sum()).pvalue
     assert pv > 1e-3, pv
     assert 0.0 < st2.acceptance <= 1.0
+
+
+# ----------------------------------------------------------------------------------------- theta GEMM (tcgen05)
+@pytest.mark.parametrize("N,M,B,bias", [(100, 400, 1000, True), (100, 400, 65, False), (20, 20, 300, True), (16, 64, 128, True),
+                                         (128, 512, 257, True), (37, 112, 129, True), (100, 400, 5000, True)])
+def test_theta_gemm_tensor_core(cuda, N, M, B, bias):
+    """nk_theta_gemm (tcgen05, exact 3-way bf16 split of W) vs the oracle's fp64 theta: fp32 accuracy, any row/column tail."""
+    import ctypes as C
+
+    from netket_b200 import _lib
+
+    rs = np.random.default_rng(7)
+    W = (rs.normal(size=(N, M)) * 0.3).astype(np.float32)
+    b = rs.normal(size=M).astype(np.float32) if bias else None
+    sig = _sigma(B, N, seed=2)
+    Wt, st = torch.from_numpy(W).cuda(), torch.from_numpy(sig).cuda()
+    bt = torch.from_numpy(b).cuda() if bias else None
+    rbm = _lib.nk_rbm_t(W=Wt.data_ptr(), b=bt.data_ptr() if bias else None, a=None, N=N, M=M, dtype=0, reserved=0)
+    L = _lib.lib()
+    ws = torch.empty(int(L.nk_theta_gemm_workspace_bytes(C.byref(rbm), B)), dtype=torch.uint8, device="cuda")
+    theta = torch.full((B, M), float("nan"), dtype=torch.float32, device="cuda")
+    _lib.check(L.nk_theta_gemm(_lib.stream_ptr(), C.byref(rbm), _lib.ptr(st), B, _lib.ptr(theta), _lib.ptr(ws)))
+    ref = orbm.theta(sig, W.astype(np.float64), None if b is None else b.astype(np.float64))
+    got = theta.cpu().numpy()
+    assert np.isfinite(got).all()
+    np.testing.assert_allclose(got, ref, rtol=2e-6, atol=2e-6 * np.abs(ref).max())
