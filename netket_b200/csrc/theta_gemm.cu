@@ -28,7 +28,7 @@ struct TcGeom {
   size_t img_bytes;    // 3 parts
   size_t a_bytes;      // A tile (128 rows)
   size_t smem_bytes;
-  int tmem_cols;
+  int tmem_cols, acc_cols;
 };
 
 static bool tc_geometry(const nk_rbm_t &rbm, TcGeom *g) {
@@ -41,8 +41,9 @@ static bool tc_geometry(const nk_rbm_t &rbm, TcGeom *g) {
   g->part_bytes = (size_t)(g->NT / 8) * g->sbo;
   g->img_bytes = 3 * g->part_bytes;
   g->a_bytes = (size_t)16 * g->sbo;
-  g->smem_bytes = g->img_bytes + g->a_bytes + 64;
-  g->tmem_cols = g->NT <= 32 ? 32 : (g->NT <= 64 ? 64 : (g->NT <= 128 ? 128 : 256));
+  g->smem_bytes = g->img_bytes + 2 * g->a_bytes + 64;  // double-buffered A tile
+  g->acc_cols = g->NT <= 32 ? 32 : (g->NT <= 64 ? 64 : (g->NT <= 128 ? 128 : 256));
+  g->tmem_cols = 2 * g->acc_cols;  // two accumulators: MMA of block k+1 overlaps the epilogue of block k
   return g->smem_bytes <= 220 * 1024 && g->img_bytes < (1u << 20);
 }
 
@@ -97,7 +98,7 @@ struct TcArgs {
   const float *bias;
   float *theta;
   int64_t B;
-  int N, M, kpad, nt, NT, sbo, tmem_cols;
+  int N, M, kpad, nt, NT, sbo, tmem_cols, acc_cols, vec_ok;
   uint32_t part_bytes, img_bytes;
 };
 
@@ -124,10 +125,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[32]) {
 __global__ void __launch_bounds__(128, 1) theta_tc_kernel(const __grid_constant__ TcArgs p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char *b_img = smem;                          // 3 parts, K-major core-matrix layout
-  unsigned char *a_tile = smem + p.img_bytes;           // 128 x kpad bf16, same layout
-  uint64_t *bars = reinterpret_cast<uint64_t *>(a_tile + (size_t)16 * p.sbo);
-  uint64_t *bar_load = bars, *bar_mma = bars + 1;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2);
+  unsigned char *a_tiles = smem + p.img_bytes;          // 2 x (128 x kpad bf16), same layout
+  const size_t a_bytes = (size_t)16 * p.sbo;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(a_tiles + 2 * a_bytes);
+  uint64_t *bar_load = bars, *bar_mma = bars + 1;       // bar_mma[0..1]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int tile = blockIdx.x % p.nt;
   const int n0 = tile * p.NT;
@@ -135,6 +137,7 @@ __global__ void __launch_bounds__(128, 1) theta_tc_kernel(const __grid_constant_
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(bar_load)));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(bar_mma)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(bar_mma + 1)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -152,79 +155,86 @@ __global__ void __launch_bounds__(128, 1) theta_tc_kernel(const __grid_constant_
                  "l"(reinterpret_cast<const unsigned char *>(p.img) + (size_t)tile * p.img_bytes), "r"(p.img_bytes), "r"(s32(bar_load))
                  : "memory");
   }
-  {  // wait for the W image
+
+  auto wait_bar = [&](uint64_t *bar, uint32_t parity) {
     uint32_t done = 0;
     do {
       asm volatile("{\n.reg .pred q;\nmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\nselp.u32 %0, 1, 0, q;\n}\n"
                    : "=r"(done)
-                   : "r"(s32(bar_load)), "r"(0u)
+                   : "r"(s32(bar)), "r"(parity)
                    : "memory");
     } while (!done);
-  }
-
+  };
+  // A tile of row block rb into buffer `buf`: row = tid, sigma int8 -> bf16 (+1 = 0x3F80, -1 = 0xBF80), zero beyond N / B
+  auto build_a = [&](int64_t rb, int buf) {
+    const int64_t row = rb * 128 + tid;
+    const int8_t *src = p.sigma + row * p.N;
+    unsigned char *dst = a_tiles + buf * a_bytes + (size_t)(tid >> 3) * p.sbo + (size_t)(tid & 7) * 16;
+    for (int c = 0; c < p.kpad / 8; ++c) {
+      uint32_t w[4] = {0u, 0u, 0u, 0u};
+      if (row < p.B) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int k = 8 * c + e;
+          const uint32_t h = (k < p.N) ? (src[k] < 0 ? 0xBF80u : 0x3F80u) : 0u;
+          w[e >> 1] |= h << (16 * (e & 1));
+        }
+      }
+      *reinterpret_cast<uint4 *>(dst + (size_t)c * 128) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  };
   // instruction descriptor, kind::f16: D = F32 (bit 4), A = B = BF16 (bits 7, 10), both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  // 3 bf16 parts x (kpad / 16) K-steps into accumulator `buf`, then commit -> bar_mma[buf]   (one thread)
+  auto issue_mma = [&](int buf) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t a_s = s32(a_tiles + buf * a_bytes), b_s = s32(b_img);
+    const uint32_t d_t = tmem_base + (uint32_t)(buf * p.acc_cols);
+    int first = 1;
+    for (int part = 0; part < 3; ++part) {
+      for (int ks = 0; ks < p.kpad / 16; ++ks) {
+        const uint64_t adesc = make_smem_desc(a_s + ks * 256, 128, (uint32_t)p.sbo);
+        const uint64_t bdesc = make_smem_desc(b_s + part * p.part_bytes + ks * 256, 128, (uint32_t)p.sbo);
+        const uint32_t acc = first ? 0u : 1u;
+        asm volatile(
+            "{\n.reg .pred q;\nsetp.ne.b32 q, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, q;\n}\n" ::"r"(d_t),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+            : "memory");
+        first = 0;
+      }
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar_mma + buf)) : "memory");
+  };
+
   const int64_t n_blocks = (p.B + 127) / 128;
   const int ctas_per_tile = gridDim.x / p.nt;
-  uint32_t mma_phase = 0;
+  const int64_t rb0 = blockIdx.x / p.nt;
+  // prologue: first A tile while the W image is still in flight
+  if (rb0 < n_blocks) build_a(rb0, 0);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core (async proxy)
+  wait_bar(bar_load, 0);
+  __syncthreads();
+  if (tid == 0 && rb0 < n_blocks) issue_mma(0);
 
-  for (int64_t rb = blockIdx.x / p.nt; rb < n_blocks; rb += ctas_per_tile) {
-    // ---- A tile: row = tid of this block, sigma int8 -> bf16 (+1 = 0x3F80, -1 = 0xBF80), zero beyond N / beyond B
-    {
-      const int64_t row = rb * 128 + tid;
-      const int8_t *src = p.sigma + row * p.N;
-      unsigned char *dst = a_tile + (size_t)(tid >> 3) * p.sbo + (size_t)(tid & 7) * 16;
-      for (int c = 0; c < p.kpad / 8; ++c) {
-        uint32_t w[4] = {0u, 0u, 0u, 0u};
-        if (row < p.B) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int k = 8 * c + e;
-            const uint32_t h = (k < p.N) ? (src[k] < 0 ? 0xBF80u : 0x3F80u) : 0u;
-            w[e >> 1] |= h << (16 * (e & 1));
-          }
-        }
-        *reinterpret_cast<uint4 *>(dst + (size_t)c * 128) = make_uint4(w[0], w[1], w[2], w[3]);
-      }
+  int it = 0;
+  for (int64_t rb = rb0; rb < n_blocks; rb += ctas_per_tile, ++it) {
+    const int buf = it & 1;
+    const int64_t rb_next = rb + ctas_per_tile;
+    // ---- next block: build its A tile and start its MMAs (they run while this block's accumulator is drained)
+    if (rb_next < n_blocks) {
+      build_a(rb_next, buf ^ 1);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core (async proxy)
     __syncthreads();
-    // ---- MMAs: 3 bf16 parts x (kpad / 16) K-steps into one accumulator
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a_s = s32(a_tile), b_s = s32(b_img);
-      int first = 1;
-      for (int part = 0; part < 3; ++part) {
-        for (int ks = 0; ks < p.kpad / 16; ++ks) {
-          const uint64_t adesc = make_smem_desc(a_s + ks * 256, 128, (uint32_t)p.sbo);
-          const uint64_t bdesc = make_smem_desc(b_s + part * p.part_bytes + ks * 256, 128, (uint32_t)p.sbo);
-          const uint32_t acc = first ? 0u : 1u;
-          asm volatile(
-              "{\n.reg .pred q;\nsetp.ne.b32 q, %4, 0;\n"
-              "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, q;\n}\n" ::"r"(tmem_base),
-              "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-              : "memory");
-          first = 0;
-        }
-      }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar_mma)) : "memory");
-    }
-    {  // all threads wait for the accumulator
-      uint32_t done = 0;
-      do {
-        asm volatile("{\n.reg .pred q;\nmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\nselp.u32 %0, 1, 0, q;\n}\n"
-                     : "=r"(done)
-                     : "r"(s32(bar_mma)), "r"(mma_phase)
-                     : "memory");
-      } while (!done);
-      mma_phase ^= 1u;
-    }
+    if (tid == 0 && rb_next < n_blocks) issue_mma(buf ^ 1);
+    // ---- this block: wait for its accumulator, epilogue: warp w owns TMEM lanes 32w..32w+31 = rows 32w..32w+31
+    wait_bar(bar_mma + buf, (uint32_t)((it >> 1) & 1));
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // ---- epilogue: warp w owns TMEM lanes 32w..32w+31 = rows 32w..32w+31 of the block
     {
       const int64_t row = rb * 128 + tid;
       float *out = p.theta + row * p.M;
-      const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * p.acc_cols);
       for (int c0 = 0; c0 < p.NT; c0 += 32) {
         uint32_t r[32];
         const int width = min(32, p.NT - c0);
@@ -234,25 +244,37 @@ __global__ void __launch_bounds__(128, 1) theta_tc_kernel(const __grid_constant_
           tmem_ld16(lane_addr + c0, r);  // NT is a multiple of 16
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (row < p.B) {
-          if (width == 32) {
+          const int jbase = n0 + c0;
+          if (p.vec_ok && jbase + width <= p.M) {
+            // 128-bit stores: this thread owns `width` consecutive floats of its row
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const int j = n0 + c0 + e;
-              if (j < p.M) out[j] = __uint_as_float(r[e]) + (p.bias != nullptr ? p.bias[j] : 0.0f);
+            for (int e = 0; e < 32; e += 4) {
+              if (e < width) {
+                float4 v = make_float4(__uint_as_float(r[e]), __uint_as_float(r[e + 1]), __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
+                if (p.bias != nullptr) {
+                  const float4 bb = *reinterpret_cast<const float4 *>(p.bias + jbase + e);
+                  v.x += bb.x;
+                  v.y += bb.y;
+                  v.z += bb.z;
+                  v.w += bb.w;
+                }
+                *reinterpret_cast<float4 *>(out + jbase + e) = v;
+              }
             }
           } else {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const int j = n0 + c0 + e;
-              if (j < p.M) out[j] = __uint_as_float(r[e]) + (p.bias != nullptr ? p.bias[j] : 0.0f);
+            for (int e = 0; e < 32; ++e) {
+              const int j = jbase + e;
+              if (e < width && j < p.M) out[j] = __uint_as_float(r[e]) + (p.bias != nullptr ? p.bias[j] : 0.0f);
             }
           }
         }
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();  // TMEM and the A tile are free again
+    // the next iteration's __syncthreads orders these TMEM reads before accumulator `buf` is overwritten
   }
+  __syncthreads();
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
@@ -293,6 +315,9 @@ int theta_gemm(cudaStream_t stream, const nk_rbm_t &rbm, const int8_t *sigma, in
   a.NT = g.NT;
   a.sbo = g.sbo;
   a.tmem_cols = g.tmem_cols;
+  a.acc_cols = g.acc_cols;
+  a.vec_ok = (rbm.M % 4 == 0) && ((reinterpret_cast<uintptr_t>(theta_out) & 15) == 0) &&
+             (rbm.b == nullptr || (reinterpret_cast<uintptr_t>(rbm.b) & 15) == 0);
   a.part_bytes = (uint32_t)g.part_bytes;
   a.img_bytes = (uint32_t)g.img_bytes;
   NK_CUDA_OK(cudaFuncSetAttribute(theta_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
