@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("NKB200_LIB") or os.path.join(_HERE, "lib", "libnkb200
 
 NK_F32, NK_F64 = 0, 1
 NK_RULE_LOCAL, NK_RULE_EXCHANGE = 0, 1
-NK_PATH_AUTO, NK_PATH_GENERIC, NK_PATH_FAST = 0, 1, 2
+NK_PATH_AUTO, NK_PATH_GENERIC, NK_PATH_FAST, NK_PATH_PROD = 0, 1, 2, 3
 NK_STATS_NPARTIAL = 8
 
 

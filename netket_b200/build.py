@@ -53,7 +53,7 @@ def build(force=False, verbose=False):
     """Compile every .cu under netket_b200/csrc and link netket_b200/lib/libnkb200.so."""
     os.makedirs(BUILD_DIR, exist_ok=True)
     os.makedirs(LIB_DIR, exist_ok=True)
-    stamp = os.path.join(BUILD_DIR, "digest")
+    stamp = os.path.join(LIB_DIR, "libnkb200.digest")  # travels with the .so (build/ does not: .gpurunignore)
     digest = _digest()
     if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp) and open(stamp).read() == digest:
         return LIB_PATH

@@ -117,13 +117,17 @@ int nk_random_state(void *stream, int8_t *sigma, int64_t B, int32_t N, int32_t n
   return random_state((cudaStream_t)stream, sigma, B, N, n_down, seed, chain_offset);
 }
 
-// workspace layout of the fast path: [theta: B*M floats | pad to 256] [flags: 256 B] [theta-GEMM workspace]
-static inline size_t ws_theta_bytes(const nk_rbm_t *rbm, int64_t B) { return (((size_t)B * rbm->M * 4) + 255) & ~(size_t)255; }
+// workspace layout of the product-form paths:
+//   [theta: B*M elements | pad to 256] [flags: 256 B] [G table + auxiliary tables (sweep_prod)] [theta-GEMM workspace]
+static inline size_t ws_theta_bytes(const nk_rbm_t *rbm, int64_t B) {
+  return (((size_t)B * rbm->M * (rbm->dtype == NK_F32 ? 4 : 8)) + 255) & ~(size_t)255;
+}
 
 int64_t nk_sweep_workspace_bytes(const nk_rbm_t *rbm, int64_t B) {
   if (check_rbm(rbm, "nk_sweep_workspace_bytes") || B < 0) return -1;
-  if (rbm->dtype != NK_F32) return 0;  // generic path: theta lives in shared memory for the whole call
-  return (int64_t)(ws_theta_bytes(rbm, B) + 256 + (size_t)theta_gemm_workspace_bytes(*rbm, B));
+  const size_t tables = sweep_prod_workspace_bytes(*rbm);
+  if (tables == 0 && rbm->dtype != NK_F32) return 0;  // generic path only: theta lives in shared memory for the whole call
+  return (int64_t)(ws_theta_bytes(rbm, B) + 256 + tables + (size_t)theta_gemm_workspace_bytes(*rbm, B));
 }
 
 int nk_sweep(void *stream, const nk_rbm_t *rbm, nk_chains_t *ch, const nk_sweep_t *a) {
@@ -149,7 +153,7 @@ int nk_sweep(void *stream, const nk_rbm_t *rbm, nk_chains_t *ch, const nk_sweep_
     rc = check_localop(a->localop, rbm->N, "nk_sweep");
     if (rc) return rc;
   }
-  NK_CHECK_ARG(a->path == NK_PATH_AUTO || a->path == NK_PATH_GENERIC || a->path == NK_PATH_FAST, "nk_sweep: bad path %d", a->path);
+  NK_CHECK_ARG(a->path >= NK_PATH_AUTO && a->path <= NK_PATH_PROD, "nk_sweep: bad path %d", a->path);
   if (ch->B == 0) return NK_OK;
 
   SweepKernelArgs k{};
@@ -178,23 +182,30 @@ int nk_sweep(void *stream, const nk_rbm_t *rbm, nk_chains_t *ch, const nk_sweep_
   k.eloc_out = a->eloc_out;
   k.eloc_dtype = a->eloc_dtype;
 
-  const bool fast_ok = sweep_fast_supported(k) && ch->workspace != nullptr;
-  if (a->path == NK_PATH_FAST && !fast_ok) {
-    set_error("nk_sweep: NK_PATH_FAST does not support this configuration (needs fp32, LocalRule, N<=128, M%%4==0, M<=512, the "
-              "tanh table within shared memory, Ising or no operator, and a workspace of nk_sweep_workspace_bytes())");
+  // path selection: the tuned fp32 LocalRule kernel (sweep_fast) where it applies, the general product-form kernel
+  // (sweep_prod: fp32/fp64, both rules, Ising / LocalOperator) otherwise, the theta-form generic kernel as the last resort
+  // and as the in-stream hand-over target when the weights leave the product form's range.
+  const bool have_ws = ch->workspace != nullptr;
+  const bool fast_ok = a->path != NK_PATH_PROD && sweep_fast_supported(k) && have_ws;
+  const bool prod_ok = !fast_ok && sweep_prod_supported(k) && have_ws;
+  if ((a->path == NK_PATH_FAST || a->path == NK_PATH_PROD) && !fast_ok && !prod_ok) {
+    set_error("nk_sweep: no product-form kernel for this configuration (needs N<=128, M<=512, at most 2048 exchange clusters "
+              "with at most 32 per site, 1- and 2-site operator terms, and a workspace of nk_sweep_workspace_bytes())");
     return NK_EUNSUPPORTED;
   }
-  if (a->path != NK_PATH_GENERIC && fast_ok) {
+  if (a->path != NK_PATH_GENERIC && (fast_ok || prod_ok)) {
     cudaStream_t st = (cudaStream_t)stream;
-    float *theta = reinterpret_cast<float *>(ch->workspace);
-    int *flags = reinterpret_cast<int *>(reinterpret_cast<char *>(ch->workspace) + ws_theta_bytes(rbm, ch->B));
-    void *scratch = reinterpret_cast<char *>(flags) + 256;
+    char *wsb = reinterpret_cast<char *>(ch->workspace);
+    void *theta = wsb;
+    int *flags = reinterpret_cast<int *>(wsb + ws_theta_bytes(rbm, ch->B));
+    void *tables = reinterpret_cast<char *>(flags) + 256;
+    void *scratch = reinterpret_cast<char *>(tables) + sweep_prod_workspace_bytes(*rbm);
     NK_CUDA_OK(cudaMemsetAsync(flags, 0, 256, st));
     rc = theta_gemm(st, *rbm, ch->sigma, ch->B, theta, scratch);  // theta = sigma W + b  (the only dense contraction)
     if (rc) return rc;
-    rc = sweep_fast(st, k, theta, flags);
+    rc = fast_ok ? sweep_fast(st, k, reinterpret_cast<const float *>(theta), flags) : sweep_prod(st, k, theta, flags, tables);
     if (rc == NK_OK && a->path == NK_PATH_AUTO) {
-      // weights beyond the product form's range: the fast kernel raises flags[0] and exits; this one then runs
+      // weights beyond the product form's range: the kernel raises flags[0] and exits; this one then runs
       k.run_if_flag = flags;
       rc = sweep_generic(st, k);
     }

@@ -37,5 +37,9 @@ int sweep_generic(cudaStream_t stream, const SweepKernelArgs &a);
 // sweep_fast.cu — product-form path (fp32 LocalRule, tanh table resident in shared memory)
 bool sweep_fast_supported(const SweepKernelArgs &a);
 int sweep_fast(cudaStream_t stream, const SweepKernelArgs &a, const float *theta_ws, int *flags);
+// sweep_prod.cu — general product-form path (fp32 / fp64, LocalRule / ExchangeRule, Ising / LocalOperator E_loc)
+bool sweep_prod_supported(const SweepKernelArgs &a);
+size_t sweep_prod_workspace_bytes(const nk_rbm_t &rbm);
+int sweep_prod(cudaStream_t stream, const SweepKernelArgs &a, const void *theta_ws, int *flags, void *tables_ws);
 
 }  // namespace nk

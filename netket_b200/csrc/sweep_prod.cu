@@ -1,0 +1,313 @@
+// Host side and table preparation of the general product-form sweep kernel (sweep_prod.cuh).
+//
+// prod_prep_rows<T>    one CTA per site i: G_i. = exp(-4 W_i.) padded to the kernel's row length, the per-site
+//                      constants (2 sum_j W_ij, 2 a_i and their fixed-point / exponential forms), max |W|, max_i sum_j |W_ij|
+// prod_prep_tables<T>  one CTA: ExchangeRule tables (clusters as bytes, clusters-per-site lists, fix(log2 n / machine_pow)),
+//                      Ising edges as bytes, LocalOperator tables compacted (netket/operator/_local_operator/
+//                      compile_helpers.py:29-218 layout -> sites / diag / mel / code arrays), the renormalisation period and
+//                      the decision whether the product form applies at all (flags[0] = 1 hands over to the generic kernel).
+#include <string.h>
+
+#include "sweep_prod.cuh"
+
+namespace nk {
+
+using namespace prod;
+
+template <typename T>
+__global__ void __launch_bounds__(128) prod_prep_rows(const __grid_constant__ ProdArgs p, int MP) {
+  typedef typename VecOf<T>::Rc Rc;
+  __shared__ double red[3][4];
+  const int i = blockIdx.x, N = p.s.rbm.N, M = p.s.rbm.M;
+  (void)N;
+  const T *W = reinterpret_cast<const T *>(p.s.rbm.W) + (size_t)i * M;
+  T *row = reinterpret_cast<T *>(const_cast<unsigned char *>(p.gtab) + (size_t)i * p.L.row_bytes);
+  double rs = 0.0, ra = 0.0, wm = 0.0;
+  for (int j = threadIdx.x; j < MP; j += blockDim.x) {
+    T g = T(1);  // padding: leaves every product unchanged
+    if (j < M) {
+      const T w = W[j];
+      g = Math<T>::exp(T(-4) * w);
+      rs += (double)w;
+      ra += fabs((double)w);
+      wm = fmax(wm, fabs((double)w));
+      if (!(fabs((double)w) < 1.0e30)) wm = 1.0e300;  // NaN / Inf
+    }
+    row[j] = g;
+  }
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) {
+    rs += __shfl_xor_sync(0xffffffffu, rs, m);
+    ra += __shfl_xor_sync(0xffffffffu, ra, m);
+    wm = fmax(wm, __shfl_xor_sync(0xffffffffu, wm, m));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = rs;
+    red[1][threadIdx.x >> 5] = ra;
+    red[2][threadIdx.x >> 5] = wm;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    rs = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+    ra = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+    wm = fmax(fmax(red[2][0], red[2][1]), fmax(red[2][2], red[2][3]));
+    const double LOG2E = 1.4426950408889634;
+    const double xn = 2.0 * rs;
+    const double yn = p.s.rbm.a != nullptr ? 2.0 * (double)reinterpret_cast<const T *>(p.s.rbm.a)[i] : 0.0;
+    Rc *rc = reinterpret_cast<Rc *>(const_cast<unsigned char *>(p.aux) + p.L.rc_off) + i;
+    if constexpr (sizeof(T) == 8) {
+      rc->xn = xn;
+      rc->yn = yn;
+      rc->ep = exp(xn + yn);
+      rc->em = exp(xn - yn);
+      rc->fx = __double2int_rn(fmax(fmin(LOG2E * xn * (double)PROD_FX_SCALE, 1.0e9), -1.0e9));
+      rc->fy = __double2int_rn(fmax(fmin(LOG2E * yn * (double)PROD_FX_SCALE, 1.0e9), -1.0e9));
+      rc->pad0 = rc->pad1 = 0;
+    } else {
+      rc->x2 = (float)(LOG2E * xn);
+      rc->y2 = (float)(LOG2E * yn);
+      rc->fx = __double2int_rn(fmax(fmin(LOG2E * xn * (double)PROD_FX_SCALE, 1.0e9), -1.0e9));
+      rc->fy = __double2int_rn(fmax(fmin(LOG2E * yn * (double)PROD_FX_SCALE, 1.0e9), -1.0e9));
+    }
+    // non-negative floats order like their bit patterns
+    atomicMax(p.flags + 2, __float_as_int((float)fmin(wm, 3.0e38)));
+    atomicMax(p.flags + 3, __float_as_int((float)fmin(fmax(ra, fabs(yn)), 3.0e38)));
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) prod_prep_tables(const __grid_constant__ ProdArgs p, int NE_pad) {
+  __shared__ int deg[128];
+  __shared__ int bad;
+  const SweepKernelArgs &s = p.s;
+  const ProdLayout &L = p.L;
+  unsigned char *aux = const_cast<unsigned char *>(p.aux);
+  const int N = s.rbm.N, tid = threadIdx.x, nt = blockDim.x;
+  if (tid == 0) bad = 0;
+  for (int i = tid; i < 128; i += nt) deg[i] = 0;
+  __syncthreads();
+  // ---- ExchangeRule tables
+  if (s.rule == NK_RULE_EXCHANGE) {
+    const int C = s.n_clusters;
+    uint8_t *cl = aux + L.cl_off;
+    uint32_t *adj = reinterpret_cast<uint32_t *>(aux + L.adj_off);
+    int *lg = reinterpret_cast<int *>(aux + L.lg_off);
+    for (int c = tid; c < C; c += nt) {
+      const int i = s.clusters[2 * c], j = s.clusters[2 * c + 1];
+      if (i < 0 || j < 0 || i >= N || j >= N || i == j) {
+        bad = 1;
+        continue;
+      }
+      cl[2 * c] = (uint8_t)i;
+      cl[2 * c + 1] = (uint8_t)j;
+      const int a = atomicAdd(&deg[i], 1), b = atomicAdd(&deg[j], 1);
+      if (a < PROD_ADJ_MAX) adj[i * PROD_ADJ_MAX + a] = (uint32_t)c | ((uint32_t)j << 16);
+      if (b < PROD_ADJ_MAX) adj[j * PROD_ADJ_MAX + b] = (uint32_t)c | ((uint32_t)i << 16);
+      if (a >= PROD_ADJ_MAX || b >= PROD_ADJ_MAX) bad = 1;
+    }
+    const double pw = s.machine_pow;
+    for (int n = tid; n <= C + 1; n += nt)
+      lg[n] = (n >= 1 && pw > 0.0) ? __double2int_rn(log2((double)n) / pw * (double)PROD_FX_SCALE) : 0;
+    __syncthreads();
+    uint8_t *adjdeg = aux + L.adjdeg_off;
+    for (int i = tid; i < N; i += nt) adjdeg[i] = (uint8_t)min(deg[i], PROD_ADJ_MAX);
+  }
+  // ---- Ising edges
+  if (s.eloc_kind == 1) {
+    uint8_t *edges = aux + L.edges_off;
+    for (int e = tid; e < 2 * s.ising.n_edges; e += nt) {
+      const int v = s.ising.edges[e];
+      if (v < 0 || v >= N) bad = 1;
+      edges[e] = (uint8_t)v;
+    }
+  }
+  // ---- LocalOperator: compact tables
+  if (s.eloc_kind == 2) {
+    for (int gi = 0; gi < s.localop.n_groups; ++gi) {
+      const nk_localop_group_t &G = s.localop.groups[gi];
+      const int rows = 1 << G.n_sites, ncm = G.ncmax;
+      uint8_t *sites = aux + L.lop_sites_off[gi];
+      T *dg = reinterpret_cast<T *>(aux + L.lop_diag_off[gi]);
+      T *ml = reinterpret_cast<T *>(aux + L.lop_mel_off[gi]);
+      uint8_t *cd = aux + L.lop_code_off[gi];
+      for (int o = tid; o < G.n_ops; o += nt) {
+        const int s0 = G.acting_on[o * G.n_sites], s1 = G.n_sites == 2 ? G.acting_on[o * G.n_sites + 1] : s0;
+        if (s0 < 0 || s1 < 0 || s0 >= N || s1 >= N || (G.n_sites == 2 && s0 == s1)) bad = 1;
+        sites[2 * o] = (uint8_t)s0;
+        sites[2 * o + 1] = (uint8_t)s1;
+      }
+      for (int e = tid; e < G.n_ops * rows; e += nt) dg[e] = (T)G.diag_mels[e];
+      for (int e = tid; e < G.n_ops * rows * ncm; e += nt) {
+        const int c = e % ncm, orow = e / ncm;
+        const double mel = c < G.n_conns[orow] ? G.mels[e] : 0.0;
+        const bool valid = c < G.n_conns[orow] && fabs(mel) > s.localop.mel_cutoff;
+        int code = valid ? 1 : 0;
+        if (valid) {
+          const int8_t *xp = G.x_prime + (size_t)e * G.n_sites;
+          code |= (xp[0] != 0 ? 2 : 0);
+          if (G.n_sites == 2) code |= (xp[1] != 0 ? 4 : 0);
+        }
+        ml[e] = valid ? (T)mel : T(0);
+        cd[e] = (uint8_t)code;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const float wmax = __int_as_float(p.flags[2]), rowabs = __int_as_float(p.flags[3]);
+    const float LOG2E = 1.4426950408889634f;
+    // renormalisation period r: a lane product has NE_pad factors, each within G^(+-(r+1)) of 1 after r un-normalised
+    // accepts, so NE_pad (r + 1) 4 wmax log2(e) must stay below the exponent range allowed for a lane product
+    const float per = (float)NE_pad * 4.0f * wmax * LOG2E;
+    int renorm = 32;
+    while (renorm >= 1 && (float)(renorm + 1) * per > PROD_EXP_RANGE) renorm >>= 1;
+    if (!(wmax < 1.0e30f)) renorm = 0;
+    // fp64 local energy multiplies M factors of up to two rows: keep 2 x 4 sum_j |W_ij| (+ the visible term) inside the
+    // double range with a wide margin; the per-site exponentials exp(xn +- yn) must be finite as well
+    if (sizeof(T) == 8 && !(8.0f * rowabs * LOG2E < 900.0f)) renorm = 0;
+    if (sizeof(T) == 4 && !(4.0f * rowabs * LOG2E < 2000.0f)) renorm = 0;  // fixed-point constants stay inside int32
+    p.flags[1] = renorm;
+    if (renorm < 1 || bad) p.flags[0] = 1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+struct ProdShape {
+  int nfull, tail, ne_pad, row_bytes, mp;
+};
+
+static bool prod_shape(int M, int dtype, ProdShape *ps) {
+  const int esz = dtype == NK_F32 ? 4 : 8;
+  const int chunk = 512 / esz;  // elements per 512-byte chunk
+  int nfull = M / chunk, rem = M % chunk, tail = 0;
+  if (rem == 0)
+    tail = 0;
+  else if (rem <= 32)
+    tail = 1;
+  else if (rem <= 64 && esz == 4)
+    tail = 2;
+  else {
+    nfull += 1;
+    tail = 0;
+  }
+  const int max_full = esz == 4 ? 4 : 8;
+  if (M < 1 || nfull > max_full || (nfull == max_full && tail != 0)) return false;
+  ps->nfull = nfull;
+  ps->tail = tail;
+  const int ne = (16 / esz) * nfull + tail;
+  ps->ne_pad = esz == 4 ? 2 * ((ne + 1) / 2) : ne;
+  ps->mp = 32 * (16 / esz) * nfull + 32 * tail;
+  ps->row_bytes = ps->mp * esz;
+  return true;
+}
+
+static inline int align16(int x) { return (x + 15) & ~15; }
+
+static int prod_warps(int dtype, int rule) {
+  return dtype == NK_F32 ? (rule == NK_RULE_LOCAL ? ProdWarps<float, NK_RULE_LOCAL>::value : ProdWarps<float, NK_RULE_EXCHANGE>::value)
+                         : (rule == NK_RULE_LOCAL ? ProdWarps<double, NK_RULE_LOCAL>::value : ProdWarps<double, NK_RULE_EXCHANGE>::value);
+}
+
+static bool prod_layout(const SweepKernelArgs &a, const ProdShape &ps, ProdLayout *L) {
+  const int esz = a.rbm.dtype == NK_F32 ? 4 : 8;
+  const int N = a.rbm.N;
+  memset(L, 0, sizeof(*L));
+  L->row_bytes = ps.row_bytes;
+  L->warps = prod_warps(a.rbm.dtype, a.rule);
+  int off = 0;
+  L->rc_off = off;
+  L->rc_stride = esz == 4 ? (int)sizeof(RcF) : (int)sizeof(RcD);
+  off = align16(off + N * L->rc_stride);
+  if (a.rule == NK_RULE_EXCHANGE) {
+    const int C = a.n_clusters;
+    L->lg_off = off;
+    off = align16(off + (C + 2) * 4);
+    L->cl_off = off;
+    off = align16(off + 2 * C);
+    L->adjdeg_off = off;
+    off = align16(off + N);
+    L->adj_off = off;
+    off = align16(off + N * PROD_ADJ_MAX * 4);
+  }
+  if (a.eloc_kind == 1) {
+    L->edges_off = off;
+    off = align16(off + 2 * a.ising.n_edges);
+  }
+  if (a.eloc_kind == 2) {
+    for (int gi = 0; gi < a.localop.n_groups; ++gi) {
+      const nk_localop_group_t &G = a.localop.groups[gi];
+      const int64_t rows = 1 << G.n_sites;
+      const int64_t total = (int64_t)G.n_ops * rows * (G.ncmax + 1) * (esz + 1);
+      if (total > PROD_AUX_MAX) return false;
+      L->lop_sites_off[gi] = off;
+      off = align16(off + 2 * G.n_ops);
+      L->lop_diag_off[gi] = off;
+      off = align16(off + (int)(G.n_ops * rows) * esz);
+      L->lop_mel_off[gi] = off;
+      off = align16(off + (int)(G.n_ops * rows * G.ncmax) * esz);
+      L->lop_code_off[gi] = off;
+      off = align16(off + (int)(G.n_ops * rows * G.ncmax));
+    }
+  }
+  if (off > PROD_AUX_MAX) return false;
+  L->aux_bytes = off;
+  const int hop_bytes = a.rule == NK_RULE_EXCHANGE ? L->warps * PROD_HOP_WORDS * 4 : 0;
+  const int fixed = L->aux_bytes + hop_bytes + 16;
+  const int budget = 227 * 1024 - fixed;
+  if (budget < 0) return false;
+  int n_res = budget / ps.row_bytes;
+  if (n_res > N) n_res = N;
+  L->n_res = n_res;
+  L->g_bytes = n_res * ps.row_bytes;
+  L->hop_off = L->g_bytes + L->aux_bytes;
+  L->bar_off = L->hop_off + hop_bytes;
+  L->smem_bytes = L->bar_off + 16;
+  return true;
+}
+
+bool sweep_prod_supported(const SweepKernelArgs &a) {
+  ProdShape ps;
+  ProdLayout L;
+  if (a.rbm.N > 128 || !prod_shape(a.rbm.M, a.rbm.dtype, &ps)) return false;
+  if (a.rule == NK_RULE_EXCHANGE && (a.n_clusters < 1 || a.n_clusters > 32 * PROD_HOP_WORDS)) return false;
+  if (a.eloc_kind == 1 && a.ising.n_edges > 8192) return false;
+  if (a.B >= (1ll << 31) || (int64_t)(a.n_discard + a.chain_length) * a.sweep_size >= (1ll << 31)) return false;  // 32-bit counters
+  return prod_layout(a, ps, &L);
+}
+
+// bytes of workspace behind theta and the flags: the G table and the aux blob
+size_t sweep_prod_workspace_bytes(const nk_rbm_t &rbm) {
+  ProdShape ps;
+  if (rbm.N > 128 || !prod_shape(rbm.M, rbm.dtype, &ps)) return 0;
+  return (((size_t)rbm.N * ps.row_bytes + 255) & ~(size_t)255) + PROD_AUX_MAX;
+}
+
+int sweep_prod(cudaStream_t stream, const SweepKernelArgs &a, const void *theta_ws, int *flags, void *tables_ws) {
+  ProdShape ps;
+  ProdArgs pa{};
+  if (!prod_shape(a.rbm.M, a.rbm.dtype, &ps) || !prod_layout(a, ps, &pa.L)) {
+    set_error("sweep_prod: unsupported configuration");
+    return NK_EUNSUPPORTED;
+  }
+  pa.s = a;
+  pa.gtab = reinterpret_cast<const unsigned char *>(tables_ws);
+  pa.aux = pa.gtab + (((size_t)a.rbm.N * ps.row_bytes + 255) & ~(size_t)255);
+  pa.theta = theta_ws;
+  pa.flags = flags;
+  if (a.rbm.dtype == NK_F32) {
+    prod_prep_rows<float><<<a.rbm.N, 128, 0, stream>>>(pa, ps.mp);
+    NK_LAUNCH_OK();
+    prod_prep_tables<float><<<1, 256, 0, stream>>>(pa, ps.ne_pad);
+    NK_LAUNCH_OK();
+    return a.rule == NK_RULE_LOCAL ? launch_prod_f32_local(stream, pa, ps.nfull, ps.tail)
+                                   : launch_prod_f32_exchange(stream, pa, ps.nfull, ps.tail);
+  }
+  prod_prep_rows<double><<<a.rbm.N, 128, 0, stream>>>(pa, ps.mp);
+  NK_LAUNCH_OK();
+  prod_prep_tables<double><<<1, 256, 0, stream>>>(pa, ps.ne_pad);
+  NK_LAUNCH_OK();
+  return a.rule == NK_RULE_LOCAL ? launch_prod_f64_local(stream, pa, ps.nfull, ps.tail)
+                                 : launch_prod_f64_exchange(stream, pa, ps.nfull, ps.tail);
+}
+
+}  // namespace nk

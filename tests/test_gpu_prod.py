@@ -1,0 +1,269 @@
+"""Parity of the general product-form sweep kernel (sweep_prod: fp32 / fp64, LocalRule / ExchangeRule, fused Ising /
+LocalOperator local energy; NK_PATH_PROD = 3) against the CPU oracle.
+
+fp64: chains identical to the oracle's (the kernel re-decides in full double precision every proposal whose fixed-point
+test is inside the approximation's error band), log-probabilities and E_loc to 1e-10 / 1e-11 relative (the running
+(A, B) pairs accumulate one rounding per accepted move).  fp32: chains identical up to accept-boundary ties, E_loc 1e-5.
+"""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import estimators as oest
+from oracle import graph as ograph
+from oracle import hilbert as ohilbert
+from oracle import operators as oops
+from oracle import rbm as orbm
+from oracle import rng as orng
+from oracle import sampler as osampler
+
+pytestmark = pytest.mark.gpu
+
+PROD = 3  # NK_PATH_PROD
+
+
+def _nk():
+    import netket_b200 as nk
+
+    return nk
+
+
+def _params(N, alpha, dtype, std=0.01, seed=1234):
+    W, b, a = orbm.init_params(N, alpha, seed=seed, std=std, dtype=dtype)
+    var = {"params": {"Dense": {"kernel": torch.from_numpy(W).cuda(), "bias": torch.from_numpy(b).cuda()},
+                      "visible_bias": torch.from_numpy(a).cuda()}}
+    return (W, b, a), var
+
+
+def _f64(*xs):
+    return tuple(x.astype(np.float64) for x in xs)
+
+
+def _case(nk, rule, L, n_dim, alpha, dtype, std, B, total_sz=None, d_max=1, sweep_size=None):
+    g = nk.graph.Hypercube(L, n_dim)
+    N = g.n_nodes
+    hi = nk.hilbert.Spin(0.5, N, total_sz=total_sz)
+    (W, b, a), var = _params(N, alpha, dtype, std)
+    model = nk.models.RBM(alpha=alpha, param_dtype=dtype)
+    e, col = ograph.hypercube_edges(L, n_dim)
+    if rule == "local":
+        sa = nk.sampler.MetropolisLocal(hi, n_chains=B, sweep_size=sweep_size)
+        clusters = None
+    else:
+        sa = nk.sampler.MetropolisExchange(hi, graph=g, d_max=d_max, n_chains=B, sweep_size=sweep_size)
+        clusters = ograph.compute_clusters(N, e, d_max)
+        assert np.array_equal(clusters, sa.rule.clusters)
+    return g, hi, (W, b, a), var, model, sa, clusters, e, col
+
+
+# ----------------------------------------------------------------------------------------- fp64 chains
+@pytest.mark.parametrize("rule,L,n_dim,alpha,std,total_sz,d_max", [
+    ("local", 20, 1, 1, 0.01, None, 1), ("local", 20, 1, 1, 0.3, None, 1), ("local", 16, 1, 2, 0.6, None, 1),
+    ("local", 10, 2, 4, 0.01, None, 1), ("local", 10, 2, 4, 0.1, None, 1), ("local", 6, 2, 3, 0.05, None, 1),
+    ("exchange", 22, 1, 2, 0.01, 0, 1), ("exchange", 12, 1, 2, 0.5, 0, 2), ("exchange", 10, 1, 1, 0.4, 1, 2),
+    ("exchange", 4, 2, 4, 0.1, 0, 2), ("exchange", 10, 2, 4, 0.02, 0, 1), ("exchange", 6, 2, 2, 0.05, 0, 2)])
+def test_prod_reproduces_oracle_chain_fp64(cuda, rule, L, n_dim, alpha, std, total_sz, d_max):
+    nk = _nk()
+    B, CL = 24, 3
+    g, hi, (W, b, a), var, model, sa, clusters, e, col = _case(nk, rule, L, n_dim, alpha, np.float64, std, B, total_sz, d_max)
+    st = sa.init_state(model, var, seed=15324)
+    sig0 = st.σ.cpu().numpy()
+    seed, t0 = st.rng
+    ref = osampler.sample_chain(rule, sig0, W, b, a, chain_length=CL, seed=seed, t0=t0, clusters=clusters)
+    (samples, logp), st2 = sa.sample(model, var, state=st, chain_length=CL, return_log_probabilities=True, _path=PROD)
+    assert np.array_equal(samples.cpu().numpy(), ref["samples"])
+    scale = max(1.0, np.abs(ref["log_prob_samples"]).max())
+    np.testing.assert_allclose(logp.cpu().numpy(), ref["log_prob_samples"], rtol=1e-10, atol=1e-11 * scale)
+    np.testing.assert_allclose(st2.log_prob.cpu().numpy(), ref["log_prob"], rtol=1e-10, atol=1e-11 * scale)
+    assert np.array_equal(st2.n_accepted_proc.cpu().numpy(), ref["n_accepted"])
+    assert st2.n_steps_proc == ref["n_steps"] and st2.rng == (seed, ref["t"])
+    assert np.array_equal(st.σ.cpu().numpy(), sig0), "input state must not be mutated"
+    assert np.array_equal(st2.σ.cpu().numpy(), ref["sigma"])
+    # continuing from the new state continues the same Philox stream
+    ref2 = osampler.sample_chain(rule, ref["sigma"], W, b, a, chain_length=2, seed=seed, t0=ref["t"], clusters=clusters)
+    s2, _ = sa.sample(model, var, state=st2, chain_length=2, _path=PROD)
+    assert np.array_equal(s2.cpu().numpy(), ref2["samples"])
+    # explicit proposal stream
+    T = CL * sa.sweep_size
+    rs = np.random.default_rng(5)
+    w0 = rs.integers(0, 2 ** 32, size=(T, B), dtype=np.uint64).astype(np.uint32)
+    u = rs.random((T, B))
+    ref3 = osampler.sample_chain(rule, sig0, W, b, a, chain_length=CL, stream=(w0, u), clusters=clusters)
+    s3, _ = sa.sample(model, var, state=st, chain_length=CL, _stream=(w0, u), _path=PROD)
+    assert np.array_equal(s3.cpu().numpy(), ref3["samples"])
+    # AUTO takes the same kernel for fp64
+    s4, _ = sa.sample(model, var, state=st, chain_length=CL, _path=0)
+    assert np.array_equal(s4.cpu().numpy(), ref["samples"])
+
+
+def test_prod_sweep_size_discard_and_machine_pow(cuda):
+    nk = _nk()
+    g, hi, (W, b, a), var, model, sa, _, e, col = _case(nk, "local", 10, 1, 1, np.float64, 0.3, 8, sweep_size=7)
+    st = sa.init_state(model, var, seed=1)
+    seed, t0 = st.rng
+    ref = osampler.sample_chain("local", st.σ.cpu().numpy(), W, b, a, chain_length=5, sweep_size=7, seed=seed, t0=t0)
+    samples, _, _, st2 = sa._launch(model, var, st, 3, n_discard=2, path=PROD)
+    assert np.array_equal(samples.cpu().numpy(), ref["samples"][:, 2:, :])
+    assert np.array_equal(st2.n_accepted_proc.cpu().numpy(), ref["n_accepted"])
+    assert st2.n_steps_proc == 8 * 5 * 7
+    sa1 = nk.sampler.MetropolisLocal(hi, n_chains=8, machine_pow=1.0)
+    st = sa1.init_state(model, var, seed=2)
+    seed, t0 = st.rng
+    ref = osampler.sample_chain("local", st.σ.cpu().numpy(), W, b, a, chain_length=4, seed=seed, t0=t0, machine_pow=1.0)
+    samples, _ = sa1.sample(model, var, state=st, chain_length=4, _path=PROD)
+    assert np.array_equal(samples.cpu().numpy(), ref["samples"])
+
+
+# ----------------------------------------------------------------------------------------- fp32 chains
+@pytest.mark.parametrize("rule,L,n_dim,alpha,std,total_sz,d_max", [
+    ("local", 20, 1, 1, 0.3, None, 1), ("local", 10, 2, 4, 0.05, None, 1), ("exchange", 12, 1, 2, 0.5, 0, 2),
+    ("exchange", 10, 2, 4, 0.02, 0, 1), ("exchange", 4, 2, 3, 0.2, 0, 2)])
+def test_prod_follows_oracle_chain_fp32(cuda, rule, L, n_dim, alpha, std, total_sz, d_max):
+    """Same Philox stream => same chains as the fp64 oracle except at fp32 accept-boundary ties."""
+    nk = _nk()
+    B, CL = 96, 2
+    g, hi, (W, b, a), var, model, sa, clusters, e, col = _case(nk, rule, L, n_dim, alpha, np.float32, std, B, total_sz, d_max)
+    st = sa.init_state(model, var, seed=7)
+    seed, t0 = st.rng
+    words, u32 = orng.proposal_stream(seed, t0, CL * hi.size, np.arange(B), np.float32)
+    W64, b64, a64 = _f64(W, b, a)
+    ref = osampler.sample_chain(rule, st.σ.cpu().numpy(), W64, b64, a64, chain_length=CL, stream=(words[..., 0], u32.astype(np.float64)),
+                                clusters=clusters)
+    (samples, logp), st2 = sa.sample(model, var, state=st, chain_length=CL, return_log_probabilities=True, _path=PROD)
+    same = np.all(samples.cpu().numpy() == ref["samples"], axis=(1, 2))
+    assert same.mean() >= 0.9, same.mean()
+    np.testing.assert_allclose(logp.cpu().numpy()[same], ref["log_prob_samples"][same], rtol=2e-5, atol=2e-4)
+    assert np.array_equal(st2.n_accepted_proc.cpu().numpy()[same], ref["n_accepted"][same])
+    assert np.array_equal(st2.σ.cpu().numpy(), samples[:, -1].cpu().numpy())
+    if total_sz is not None:
+        assert np.all(samples.cpu().numpy().astype(int).sum(axis=-1) == round(2 * total_sz))
+
+
+# ----------------------------------------------------------------------------------------- fused E_loc
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("L,n_dim,alpha,std,h,CL", [(10, 2, 4, 0.01, 3.0, 3), (10, 2, 4, 0.1, 3.0, 3), (20, 1, 1, 0.2, 1.0, 6),
+                                                     (4, 2, 2, 0.3, 0.5, 8), (6, 1, 1, 0.3, 0.0, 2), (10, 2, 4, 0.05, 3.0, 24)])
+def test_prod_fused_eloc_ising(cuda, dtype, L, n_dim, alpha, std, h, CL):
+    nk = _nk()
+    B = 40
+    g, hi, (W, b, a), var, model, sa, _, e, col = _case(nk, "local", L, n_dim, alpha, dtype, std, B)
+    op = nk.operator.Ising(hi, g, h=h)
+    st = sa.init_state(model, var, seed=11)
+    samples, _, eloc, st2 = sa._launch(model, var, st, CL, n_discard=1, operator=op, path=PROD)
+    W64, b64, a64 = _f64(W, b, a)
+    ref = oest.local_estimators(samples.cpu().numpy(), lambda x: oops.ising_conn_padded(x, e, h, 1.0), W64, b64, a64)
+    assert eloc.dtype == torch.float64
+    tol = 1e-11 if dtype == np.float64 else 1e-5
+    np.testing.assert_allclose(eloc.cpu().numpy(), ref, rtol=tol, atol=tol * np.abs(ref).max())
+
+
+def _heis(nk, L, n_dim, total_sz, J, sign_rule, order=1):
+    g = nk.graph.Hypercube(L, n_dim, pbc=True, max_neighbor_order=order)
+    hi = nk.hilbert.Spin(0.5, g.n_nodes, total_sz=total_sz)
+    op = nk.operator.Heisenberg(hi, g, J=J, sign_rule=sign_rule)
+    e, c = ograph.hypercube_edges(L, n_dim, max_neighbor_order=order)
+    sr = sign_rule
+    if sr is None:
+        sr = [False] * len(J) if isinstance(J, (list, tuple)) else ograph.is_bipartite(g.n_nodes, e)
+    tables = oops.heisenberg_tables(e, c, J=J, sign_rule=sr)
+    return g, hi, op, tables
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("rule,L,n_dim,total_sz,J,sign_rule,order,alpha,std", [
+    ("exchange", 12, 1, 0, 1.0, None, 1, 2, 0.2), ("exchange", 22, 1, 0, 1.0, None, 1, 2, 0.01),
+    ("exchange", 10, 2, 0, [1.0, 0.5], None, 2, 4, 0.03), ("local", 4, 2, None, 1.0, True, 1, 1, 0.4),
+    ("exchange", 6, 1, 0, [1.0, 2.0], [True, False], 2, 3, 0.1)])
+def test_prod_fused_eloc_heisenberg(cuda, dtype, rule, L, n_dim, total_sz, J, sign_rule, order, alpha, std):
+    """cfg-2 / cfg-4 shapes: Heisenberg and J1-J2 bond operators (LocalOperator tables) fused into the sweep kernel."""
+    nk = _nk()
+    g, hi, op, tables = _heis(nk, L, n_dim, total_sz, J, sign_rule, order)
+    N = g.n_nodes
+    (W, b, a), var = _params(N, alpha, dtype, std)
+    model = nk.models.RBM(alpha=alpha, param_dtype=dtype)
+    sa = (nk.sampler.MetropolisExchange(hi, graph=g, n_chains=20) if rule == "exchange" else nk.sampler.MetropolisLocal(hi, n_chains=20))
+    st = sa.init_state(model, var, seed=5)
+    samples, _, eloc, _ = sa._launch(model, var, st, 4, n_discard=1, operator=op, path=PROD)
+    W64, b64, a64 = _f64(W, b, a)
+    ref = oest.local_estimators(samples.cpu().numpy(), lambda x: oops.local_operator_conn_padded(x, tables), W64, b64, a64)
+    tol = 1e-11 if dtype == np.float64 else 2e-5
+    np.testing.assert_allclose(eloc.cpu().numpy(), ref, rtol=tol, atol=tol * np.abs(ref).max())
+    if total_sz is not None:
+        assert np.all(samples.cpu().numpy().astype(int).sum(axis=-1) == round(2 * total_sz))
+    # the generic kernel on the same start state and stream gives the same chain in fp64, hence the same E_loc
+    if dtype == np.float64:
+        s_gen, _, e_gen, _ = sa._launch(model, var, st, 4, n_discard=1, operator=op, path=1)
+        assert np.array_equal(s_gen.cpu().numpy(), samples.cpu().numpy())
+        np.testing.assert_allclose(eloc.cpu().numpy(), e_gen.cpu().numpy(), rtol=1e-10, atol=1e-10 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_prod_fused_eloc_general_local_operator(cuda, dtype):
+    """1-site + 2-site terms with arbitrary (symmetric) matrices: single flips, exchange-like and same-sign double flips,
+    entries that map sigma onto itself do not occur off the diagonal; several entries per row (ncmax = 3)."""
+    nk = _nk()
+    N = 6
+    hi = nk.hilbert.Spin(0.5, N)
+    rs = np.random.default_rng(0)
+    ops, aon = [], []
+    for i in range(N):
+        m = rs.normal(size=(2, 2)); ops.append(m + m.T); aon.append([i])
+    for (i, j) in [(0, 1), (2, 1), (5, 3), (1, 0), (4, 5)]:
+        m = rs.normal(size=(4, 4)); m[np.abs(m) < 0.4] = 0.0; ops.append(m + m.T); aon.append([i, j])
+    op = nk.operator.LocalOperator(hi, ops, aon, constant=0.3)
+    tables = oops.pack_internals(oops.canonical_operators_dict(ops, aon), 0.3)
+    (W, b, a), var = _params(N, 3, dtype, 0.3)
+    model = nk.models.RBM(alpha=3, param_dtype=dtype)
+    sa = nk.sampler.MetropolisLocal(hi, n_chains=64)
+    st = sa.init_state(model, var, seed=9)
+    samples, _, eloc, _ = sa._launch(model, var, st, 3, operator=op, path=PROD)
+    W64, b64, a64 = _f64(W, b, a)
+    ref = oest.local_estimators(samples.cpu().numpy(), lambda x: oops.local_operator_conn_padded(x, tables), W64, b64, a64)
+    tol = 1e-11 if dtype == np.float64 else 2e-5
+    np.testing.assert_allclose(eloc.cpu().numpy(), ref, rtol=tol, atol=tol * np.abs(ref).max())
+
+
+# ----------------------------------------------------------------------------------------- hand-over, statistics
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("rule", ["local", "exchange"])
+def test_prod_hands_over_to_generic_for_large_weights(cuda, dtype, rule):
+    nk = _nk()
+    g, hi, (W, b, a), var, model, sa, clusters, e, col = _case(nk, rule, 4, 2, 16, dtype, 1.5, 32, 0 if rule == "exchange" else None, 1)
+    assert np.abs(W).max() > 4.0
+    op = nk.operator.Ising(hi, g, h=1.0)
+    st = sa.init_state(model, var, seed=3)
+    s_auto, _, e_auto, st_a = sa._launch(model, var, st, 3, operator=op, path=0)
+    s_gen, _, e_gen, st_g = sa._launch(model, var, st, 3, operator=op, path=1)
+    assert np.array_equal(s_auto.cpu().numpy(), s_gen.cpu().numpy())
+    assert np.array_equal(e_auto.cpu().numpy(), e_gen.cpu().numpy())
+    assert np.array_equal(st_a.n_accepted_proc.cpu().numpy(), st_g.n_accepted_proc.cpu().numpy())
+
+
+@pytest.mark.parametrize("dtype,rule,std", [(np.float32, "exchange", 0.3), (np.float64, "exchange", 0.3), (np.float64, "local", 0.4),
+                                            (np.float32, "local", 0.05)])
+def test_prod_sampler_chi_square(cuda, dtype, rule, std):
+    """test/sampler/test_sampler.py:399-457: histogram vs exact |psi|^2 (6 sites; the exchange rule stays in total_sz = 0)."""
+    from scipy import stats as sstats
+
+    nk = _nk()
+    N = 6
+    g = nk.graph.Chain(N)
+    total_sz = 0 if rule == "exchange" else None
+    hi = nk.hilbert.Spin(0.5, N, total_sz=total_sz)
+    (W, b, a), var = _params(N, 2, dtype, std)
+    model = nk.models.RBM(alpha=2, param_dtype=dtype)
+    sa = (nk.sampler.MetropolisExchange(hi, graph=g, d_max=2, n_chains=512, sweep_size=8) if rule == "exchange"
+          else nk.sampler.MetropolisLocal(hi, n_chains=512, sweep_size=8))
+    st = sa.init_state(model, var, seed=5)
+    samples, _, _, st2 = sa._launch(model, var, st, 100, n_discard=20, path=PROD)
+    states = ohilbert.all_states(N)
+    if total_sz is not None:
+        states = states[states.astype(int).sum(axis=1) == 0]
+    p = osampler.exact_distribution(*_f64(W, b, a), states)
+    thin = samples[:, ::4].cpu().numpy().reshape(-1, N)
+    idx = {tuple(s): k for k, s in enumerate(states)}
+    counts = np.bincount([idx[tuple(s)] for s in thin], minlength=len(states))
+    pv = sstats.chisquare(counts, p * counts.sum()).pvalue
+    assert pv > 1e-3, pv
+    assert 0.0 < st2.acceptance <= 1.0
