@@ -257,6 +257,7 @@ static bool prod_layout(const SweepKernelArgs &a, const ProdShape &ps, ProdLayou
   if (budget < 0) return false;
   int n_res = budget / ps.row_bytes;
   if (n_res > N) n_res = N;
+  if (esz == 4 && n_res < N) return false;  // fp32 kernels read the table with explicit shared-memory loads only
   L->n_res = n_res;
   L->g_bytes = n_res * ps.row_bytes;
   L->hop_off = L->g_bytes + L->aux_bytes;

@@ -206,28 +206,36 @@ __device__ __forceinline__ void load_row_s(uint32_t row_lane, uint32_t tail_lane
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(g[2 * q]), "=d"(g[2 * q + 1]) : "r"(row_lane + 512 * q));
   if (TAIL == 1) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(g[2 * NFULL]) : "r"(tail_lane));
 }
+// generic-address loads: one code path for rows resident in shared memory and rows read through L2 (the address
+// is selected, not the instruction, so nothing is issued twice under predication)
 template <int NFULL, int TAIL>
-__device__ __forceinline__ void load_row_g(const unsigned char *row_lane, const unsigned char *tail_lane,
+__device__ __forceinline__ void load_row_p(const unsigned char *row_lane, const unsigned char *tail_lane,
                                            float2 (&g)[LaneMap<float, NFULL, TAIL>::NV]) {
 #pragma unroll
   for (int q = 0; q < NFULL; ++q) {
-    const float4 v = __ldg(reinterpret_cast<const float4 *>(row_lane + 512 * q));
+    float4 v;
+    asm volatile("ld.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(row_lane + 512 * q));
     g[2 * q] = make_float2(v.x, v.y);
     g[2 * q + 1] = make_float2(v.z, v.w);
   }
-  if (TAIL == 1) g[2 * NFULL] = make_float2(__ldg(reinterpret_cast<const float *>(tail_lane)), 1.0f);
-  if (TAIL == 2) g[2 * NFULL] = __ldg(reinterpret_cast<const float2 *>(tail_lane));
+  if (TAIL == 1) {
+    float v;
+    asm volatile("ld.f32 %0, [%1];" : "=f"(v) : "l"(tail_lane));
+    g[2 * NFULL] = make_float2(v, 1.0f);
+  }
+  if (TAIL == 2) {
+    float2 v;
+    asm volatile("ld.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(tail_lane));
+    g[2 * NFULL] = v;
+  }
 }
 template <int NFULL, int TAIL>
-__device__ __forceinline__ void load_row_g(const unsigned char *row_lane, const unsigned char *tail_lane,
+__device__ __forceinline__ void load_row_p(const unsigned char *row_lane, const unsigned char *tail_lane,
                                            double (&g)[LaneMap<double, NFULL, TAIL>::NV]) {
 #pragma unroll
-  for (int q = 0; q < NFULL; ++q) {
-    const double2 v = __ldg(reinterpret_cast<const double2 *>(row_lane + 512 * q));
-    g[2 * q] = v.x;
-    g[2 * q + 1] = v.y;
-  }
-  if (TAIL == 1) g[2 * NFULL] = __ldg(reinterpret_cast<const double *>(tail_lane));
+  for (int q = 0; q < NFULL; ++q)
+    asm volatile("ld.v2.f64 {%0, %1}, [%2];" : "=d"(g[2 * q]), "=d"(g[2 * q + 1]) : "l"(row_lane + 512 * q));
+  if (TAIL == 1) asm volatile("ld.f64 %0, [%1];" : "=d"(g[2 * NFULL]) : "l"(tail_lane));
 }
 
 // prod_q hprod(X_q * g_q + Y_q), two interleaved accumulators
@@ -271,6 +279,18 @@ __device__ __forceinline__ double warp_prod(double v) {
   for (int m = 16; m > 0; m >>= 1) v *= __shfl_xor_sync(0xffffffffu, v, m);
   return v;
 }
+
+// fp64, once per chain and call: kept out of line so that the transcendental code is not replicated per hidden unit
+// (the kernel's hot loops stay small for the instruction cache)
+static __device__ __noinline__ double2 pair_from_theta(double x) {  // (e^x, e^-x) / (2 cosh x)
+  const double ex = exp(-2.0 * fabs(x));
+  const double big = 1.0 / (1.0 + ex), small = ex * big;
+  return x >= 0.0 ? make_double2(big, small) : make_double2(small, big);
+}
+static __device__ __noinline__ double lncosh_from_pair(double a, double b) {  // log((a + b) / (2 sqrt(a b)))
+  return log(a + b) - 0.5 * (log(a) + log(b)) - 0.69314718055994530942;
+}
+static __device__ __noinline__ double rcp_sum(double a, double b) { return 1.0 / (a + b); }
 
 // fp64 only, rare: the decision of a proposal whose fixed-point test fell inside the approximation's error band.
 //   accept  <=>  u < exp(machine_pow * (cst + sum_lanes log(Pprop / Pcur)) + corr)      (metropolis.py:444-450)
@@ -379,68 +399,87 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
   const T pw = (T)s.machine_pow;
   const T inv_pw = pw > T(0) ? T(1) / pw : T(0);
   const T LN2 = (T)0.69314718055994530942, LOG2E = (T)1.4426950408889634;
+  // rows: the first n_res live in shared memory, the others are read from the global table (through L2)
+  // (fp32 kernels are only launched when the whole table is resident: explicit LDS; fp64 uses generic addresses)
   uint32_t lane_row = s32(smem) + 16u * lane;
   uint32_t lane_tail = s32(smem) + (uint32_t)LM::TAIL_OFF + (uint32_t)LM::TAIL_LANE * lane;
-  const unsigned char *glane_row = p.gtab + 16 * lane;
-  const unsigned char *glane_tail = p.gtab + LM::TAIL_OFF + LM::TAIL_LANE * lane;
+  const unsigned char *sbase = smem;    // generic address of the resident rows
+  const unsigned char *gbase = p.gtab;
   int n_res = L.n_res;
   int sweep_size = s.sweep_size;
   asm volatile("" : "+r"(lane_row), "+r"(lane_tail), "+r"(n_res), "+r"(sweep_size));
 
   auto fetch = [&](int site, V(&g)[NV]) {
-    if (site < n_res) {
+    if constexpr (!F64) {
       const uint32_t o = (uint32_t)site * (uint32_t)ROW_BYTES;
       load_row_s<NFULL, TAIL>(lane_row + o, lane_tail + o, g);
     } else {
-      const size_t o = (size_t)site * ROW_BYTES;
-      load_row_g<NFULL, TAIL>(glane_row + o, glane_tail + o, g);
+      const unsigned char *row = (site < n_res ? sbase : gbase) + (size_t)site * ROW_BYTES;
+      load_row_p<NFULL, TAIL>(row + 16 * lane, row + LM::TAIL_OFF + LM::TAIL_LANE * lane, g);
     }
   };
 
   for (int chain = blockIdx.x * WARPS + warp; chain < (int)s.B; chain += gridDim.x * WARPS) {
     V A[NV], Bv[NV];
-    uint32_t sw0 = 0, sw1 = 0, sw2 = 0, sw3 = 0;  // sigma as bit words (bit set: sigma = -1), replicated in every lane
+    // sigma, lane-distributed: bit b of lane l is set iff sigma of site 32 b + l is -1
+    uint32_t mybits = 0;
     int R = 0, since = 0, n_hop = 0;
     uint32_t nacc = 0;
     {
       const int8_t *sg = s.sigma + (size_t)chain * N;
-      sw0 = __ballot_sync(FULL, lane < N && sg[lane] < 0);
-      if (N > 32) sw1 = __ballot_sync(FULL, 32 + lane < N && sg[32 + lane] < 0);
-      if (N > 64) sw2 = __ballot_sync(FULL, 64 + lane < N && sg[64 + lane] < 0);
-      if (N > 96) sw3 = __ballot_sync(FULL, 96 + lane < N && sg[96 + lane] < 0);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int idx = 32 * b + lane;
+        if (idx < N && sg[idx] < 0) mybits |= 1u << b;
+      }
     }
-    auto sbit = [&](int site) -> uint32_t { return (sel4(sw0, sw1, sw2, sw3, site >> 5) >> (site & 31)) & 1u; };
+    // spin bit of an arbitrary (warp-uniform or not) site: one shuffle
+    auto sbit = [&](int site) -> uint32_t { return (__shfl_sync(FULL, mybits, site & 31) >> (site >> 5)) & 1u; };
     auto stoggle = [&](int site) {
-      const uint32_t m = 1u << (site & 31);
-      const int w = site >> 5;
-      if (w == 0) sw0 ^= m;
-      if (w == 1) sw1 ^= m;
-      if (w == 2) sw2 ^= m;
-      if (w == 3) sw3 ^= m;
+      if (lane == (site & 31)) mybits ^= 1u << (site >> 5);
+    };
+    auto ownbit = [&](int b) -> uint32_t { return (mybits >> b) & 1u; };  // site 32 b + lane
+    // sigma as four bit words replicated in every lane (for lane-parallel table walks)
+    struct Words {
+      uint32_t w0, w1, w2, w3;
+      __device__ __forceinline__ uint32_t bit(int site) const { return (sel4(w0, w1, w2, w3, site >> 5) >> (site & 31)) & 1u; }
+    };
+    auto words = [&]() -> Words {
+      Words w;
+      w.w0 = __ballot_sync(FULL, mybits & 1u);
+      w.w1 = __ballot_sync(FULL, mybits & 2u);
+      w.w2 = __ballot_sync(FULL, mybits & 4u);
+      w.w3 = __ballot_sync(FULL, mybits & 8u);
+      return w;
     };
     // ---- theta -> (A, B) = (e^theta, e^-theta) / (2 cosh theta)
     {
       const T *th = reinterpret_cast<const T *>(p.theta) + (size_t)chain * M;
-      T av[F64 ? NV : 2 * NV], bv[F64 ? NV : 2 * NV];
+      if constexpr (F64) {
 #pragma unroll
-      for (int e = 0; e < (F64 ? NV : 2 * NV); ++e) {
-        const int j = e < NE ? LM::unit(e, lane) : M;
-        av[e] = T(0.5);
-        bv[e] = T(0.5);  // padding units: theta = 0
-        if (j < M) {
-          const T x = th[j];
-          const T ex = Math<T>::exp(T(-2) * Math<T>::abs(x));
-          const T big = T(1) / (T(1) + ex), small = ex * big;
-          av[e] = x >= T(0) ? big : small;
-          bv[e] = x >= T(0) ? small : big;
+        for (int q = 0; q < NV; ++q) {
+          const int j = LM::unit(q, lane);
+          const double2 ab = pair_from_theta(j < M ? th[j] : 0.0);  // padding units: theta = 0
+          A[q] = ab.x;
+          Bv[q] = ab.y;
         }
-      }
+      } else {
+        float av[2 * NV], bv[2 * NV];
 #pragma unroll
-      for (int q = 0; q < NV; ++q) {
-        if constexpr (F64) {
-          A[q] = av[q];
-          Bv[q] = bv[q];
-        } else {
+        for (int e = 0; e < 2 * NV; ++e) {
+          const int j = e < NE ? LM::unit(e, lane) : M;
+          av[e] = 0.5f;
+          bv[e] = 0.5f;  // padding units: theta = 0
+          if (j < M) {
+            const float x = th[j];
+            const float ex = expf(-2.0f * fabsf(x));
+            const float big = 1.0f / (1.0f + ex), small = ex * big;
+            av[e] = x >= 0.0f ? big : small;
+            bv[e] = x >= 0.0f ? small : big;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
           A[q] = make_float2(av[2 * q], av[2 * q + 1]);
           Bv[q] = make_float2(bv[2 * q], bv[2 * q + 1]);
         }
@@ -449,10 +488,11 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
     // ---- exchange: hoppable-cluster bit words of this chain (rules/exchange.py:208-218)
     if (RULE == NK_RULE_EXCHANGE) {
       __syncwarp();
+      const Words sw = words();
       for (int q = 0; q < PROD_HOP_WORDS; ++q) {
         const int c = 32 * q + lane;
         bool h = false;
-        if (c < C) h = sbit(cl[2 * c]) != sbit(cl[2 * c + 1]);
+        if (c < C) h = sw.bit(cl[2 * c]) != sw.bit(cl[2 * c + 1]);
         const uint32_t b = __ballot_sync(FULL, h);
         if (lane == 0) hopw[q] = b;
         n_hop += __popc(b);
@@ -465,7 +505,7 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
 #pragma unroll
       for (int q = 0; q < NV; ++q) {
         if constexpr (F64) {
-          const double ix = 1.0 / (A[q] + Bv[q]);
+          const double ix = rcp_sum(A[q], Bv[q]);
           A[q] *= ix;
           Bv[q] *= ix;
         } else {
@@ -490,7 +530,7 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
 #pragma unroll
       for (int q = 0; q < NV; ++q) {
         if constexpr (F64) {
-          acc += log(A[q] + Bv[q]) - 0.5 * (log(A[q]) + log(Bv[q])) - LN2;
+          acc += lncosh_from_pair(A[q], Bv[q]);
         } else {
           acc += LN2 * (log2f(A[q].x + Bv[q].x) - 0.5f * (log2f(A[q].x) + log2f(Bv[q].x)) - 1.0f);
           acc += LN2 * (log2f(A[q].y + Bv[q].y) - 0.5f * (log2f(A[q].y) + log2f(Bv[q].y)) - 1.0f);
@@ -506,7 +546,7 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
               ai = 0.5 * rctab[idx].yn;
             else
               ai = 0.5f * LN2 * rctab[idx].y2;
-            acc += sbit(idx) ? -ai : ai;
+            acc += ownbit(b) ? -ai : ai;
           }
         }
       }
@@ -612,12 +652,13 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
         nrm = warp_sum(lg2_fast(lane_norm()));
       T off_l = T(0);
       double dl = 0.0;  // diagonal, per-lane partial
+      const Words sw = words();
       // candidates are produced 32 at a time (one per lane); rounds enumerate sites (Ising) or (term, entry) slots
       int rounds0, rounds1 = 0;
       if (s.eloc_kind == 1) {
         // E_loc = J sum_<ij> s_i s_j - h sum_i psi(sigma^(i)) / psi(sigma)        (_ising/jax.py:125-165)
         int zz = 0;
-        for (int e = lane; e < E; e += 32) zz += 1 - 2 * (int)(sbit(edges[2 * e]) ^ sbit(edges[2 * e + 1]));
+        for (int e = lane; e < E; e += 32) zz += 1 - 2 * (int)(sw.bit(edges[2 * e]) ^ sw.bit(edges[2 * e + 1]));
         dl = s.ising.J * (double)zz;
         rounds0 = s.ising.h != 0.0 ? (N + 31) / 32 : 0;
       } else {
@@ -633,7 +674,7 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
         T mel = T(0);
         if (s.eloc_kind == 1) {
           const int site = 32 * r + lane;
-          if (site < N) d = CD_VALID | CD_CHG0 | (uint32_t)site | ((uint32_t)site << 8) | (sbit(site) ? CD_POS0 : 0u);
+          if (site < N) d = CD_VALID | CD_CHG0 | (uint32_t)site | ((uint32_t)site << 8) | (sw.bit(site) ? CD_POS0 : 0u);
           mel = (T)(-s.ising.h);
         } else {
           const int gi = r < rounds0 ? 0 : 1;
@@ -648,7 +689,7 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
           if (q < slots) {
             const int o = ncm > 1 ? q / ncm : q, c = ncm > 1 ? q - o * ncm : 0;
             const int s0 = sites[2 * o], s1 = sites[2 * o + 1];
-            const int x0 = (int)sbit(s0), x1 = G.n_sites == 2 ? (int)sbit(s1) : 0;
+            const int x0 = (int)sw.bit(s0), x1 = G.n_sites == 2 ? (int)sw.bit(s1) : 0;
             const int row = G.n_sites == 2 ? 2 * x0 + x1 : x0;  // _state_to_number: first site most significant
             if (c == 0) dl += (double)dg[o * rows + row];
             if (ncm > 0) {
@@ -690,7 +731,7 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
           const int idx = 32 * b + lane;
-          if (idx < N) s.samples_out[o * N + idx] = sbit(idx) ? (int8_t)-1 : (int8_t)1;
+          if (idx < N) s.samples_out[o * N + idx] = ownbit(b) ? (int8_t)-1 : (int8_t)1;
         }
       }
       if (s.logp_out != nullptr) {
@@ -868,7 +909,7 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
       const int idx = 32 * b + lane;
-      if (idx < N) s.sigma[(size_t)chain * N + idx] = sbit(idx) ? (int8_t)-1 : (int8_t)1;
+      if (idx < N) s.sigma[(size_t)chain * N + idx] = ownbit(b) ? (int8_t)-1 : (int8_t)1;
     }
     const T lp = logpsi_now();
     if (lane == 0) {
