@@ -164,11 +164,12 @@ int nk_localop_conn(void *stream, const nk_localop_t *op, const int8_t *x, int64
                     int32_t mel_dtype, int32_t *nconn_out);
 
 /* local_value_kernel_jax for (RBM, Ising) and (RBM, LocalOperator) without materialising sigma'
- * (netket/vqs/mc/kernels.py:62-71; seam S4).  eloc_out [B] (eloc_dtype). */
+ * (netket/vqs/mc/kernels.py:62-71; seam S4).  eloc_out [B] (eloc_dtype).
+ * workspace: nk_sweep_workspace_bytes(rbm, B) bytes of scratch for the product-form kernel, or NULL (theta-form kernel). */
 int nk_eloc_ising_rbm(void *stream, const nk_rbm_t *rbm, const nk_ising_t *op, const int8_t *sigma, int64_t B, void *eloc_out,
-                      int32_t eloc_dtype, int32_t path);
+                      int32_t eloc_dtype, int32_t path, void *workspace);
 int nk_eloc_localop_rbm(void *stream, const nk_rbm_t *rbm, const nk_localop_t *op, const int8_t *sigma, int64_t B, void *eloc_out,
-                        int32_t eloc_dtype);
+                        int32_t eloc_dtype, int32_t path, void *workspace);
 
 /* statistics() (netket/stats/mc_stats_old.py:52-196), split so that only scalars cross devices:
  *   phase 0: partials_out[0] = sum(x)                                    -> all-reduce -> mean

@@ -39,10 +39,7 @@ int num_sms() {
 // implemented in the other translation units
 int rbm_logpsi(cudaStream_t stream, const nk_rbm_t &rbm, const int8_t *sigma, int64_t B, void *out, void *theta_out);
 int eloc_generic(cudaStream_t stream, const nk_rbm_t &rbm, const nk_ising_t *ising, const nk_localop_t *localop,
-                 const int8_t *sigma, int64_t B, void *eloc_out, int32_t eloc_dtype);
-int eloc_fast_ising(cudaStream_t stream, const nk_rbm_t &rbm, const nk_ising_t &ising, const int8_t *sigma, int64_t B,
-                    void *eloc_out, int32_t eloc_dtype);
-bool eloc_fast_supported(const nk_rbm_t &rbm);
+                 const int8_t *sigma, int64_t B, void *eloc_out, int32_t eloc_dtype, const int *run_if_flag);
 int ising_conn(cudaStream_t stream, const nk_ising_t &op, const int8_t *x, int64_t B, int32_t N, int8_t *xp, void *mels,
                int32_t mel_dtype);
 int ising_n_conn(cudaStream_t stream, const nk_ising_t &op, const int8_t *x, int64_t B, int32_t N, int32_t *out);
@@ -243,32 +240,69 @@ int nk_localop_conn(void *stream, const nk_localop_t *op, const int8_t *x, int64
   return localop_conn((cudaStream_t)stream, *op, x, B, N, xp_out, mels_out, mel_dtype, nconn_out);
 }
 
+// Stand-alone local estimator: the product-form kernel in its `eloc_only` mode (theta GEMM, (A, B) from theta, the fused
+// local-energy code of the sweep kernel), or the theta-form generic kernel (no workspace, NK_PATH_GENERIC, or in-stream
+// hand-over when the weights are outside the product form's range).
+static int eloc_dispatch(cudaStream_t st, const nk_rbm_t *rbm, const nk_ising_t *ising, const nk_localop_t *localop,
+                         const int8_t *sigma, int64_t B, void *eloc_out, int32_t eloc_dtype, int32_t path, void *workspace,
+                         const char *who) {
+  NK_CHECK_ARG(path >= NK_PATH_AUTO && path <= NK_PATH_PROD, "%s: bad path %d", who, path);
+  if (B == 0) return NK_OK;
+  SweepKernelArgs k{};
+  k.rbm = *rbm;
+  k.sigma = const_cast<int8_t *>(sigma);  // not written in eloc_only mode
+  k.B = B;
+  k.rule = NK_RULE_LOCAL;
+  k.chain_length = 1;
+  k.n_discard = 0;
+  k.sweep_size = 1;
+  k.machine_pow = 2.0;
+  k.eloc_kind = ising ? 1 : 2;
+  if (ising) k.ising = *ising;
+  if (localop) k.localop = *localop;
+  k.eloc_out = eloc_out;
+  k.eloc_dtype = eloc_dtype;
+  k.eloc_only = 1;
+  const bool prod_ok = workspace != nullptr && sweep_prod_supported(k);
+  if ((path == NK_PATH_FAST || path == NK_PATH_PROD) && !prod_ok) {
+    set_error("%s: no product-form kernel for this configuration (needs N<=128, M<=512, 1- and 2-site operator terms and a "
+              "workspace of nk_sweep_workspace_bytes())", who);
+    return NK_EUNSUPPORTED;
+  }
+  if (path == NK_PATH_GENERIC || !prod_ok) return eloc_generic(st, *rbm, ising, localop, sigma, B, eloc_out, eloc_dtype, nullptr);
+  char *wsb = reinterpret_cast<char *>(workspace);
+  void *theta = wsb;
+  int *flags = reinterpret_cast<int *>(wsb + ws_theta_bytes(rbm, B));
+  void *tables = reinterpret_cast<char *>(flags) + 256;
+  void *scratch = reinterpret_cast<char *>(tables) + sweep_prod_workspace_bytes(*rbm);
+  NK_CUDA_OK(cudaMemsetAsync(flags, 0, 256, st));
+  int rc = theta_gemm(st, *rbm, sigma, B, theta, scratch);
+  if (rc) return rc;
+  rc = sweep_prod(st, k, theta, flags, tables);
+  if (rc == NK_OK && path == NK_PATH_AUTO) rc = eloc_generic(st, *rbm, ising, localop, sigma, B, eloc_out, eloc_dtype, flags);
+  return rc;
+}
+
 int nk_eloc_ising_rbm(void *stream, const nk_rbm_t *rbm, const nk_ising_t *op, const int8_t *sigma, int64_t B, void *eloc_out,
-                      int32_t eloc_dtype, int32_t path) {
+                      int32_t eloc_dtype, int32_t path, void *workspace) {
   int rc = check_rbm(rbm, "nk_eloc_ising_rbm");
   if (rc) return rc;
   NK_CHECK_ARG(op != nullptr, "nk_eloc_ising_rbm: operator is NULL");
   NK_CHECK_ARG(op->n_edges >= 0 && (op->n_edges == 0 || op->edges), "nk_eloc_ising_rbm: bad edges");
   NK_CHECK_ARG(B >= 0 && (B == 0 || (sigma && eloc_out)), "nk_eloc_ising_rbm: bad batch / NULL buffer");
   NK_CHECK_ARG(eloc_dtype == NK_F32 || eloc_dtype == NK_F64, "nk_eloc_ising_rbm: bad eloc_dtype");
-  const bool fast_ok = eloc_fast_supported(*rbm);
-  if (path == NK_PATH_FAST && !fast_ok) {
-    set_error("nk_eloc_ising_rbm: NK_PATH_FAST does not support this shape/dtype");
-    return NK_EUNSUPPORTED;
-  }
-  if (path != NK_PATH_GENERIC && fast_ok) return eloc_fast_ising((cudaStream_t)stream, *rbm, *op, sigma, B, eloc_out, eloc_dtype);
-  return eloc_generic((cudaStream_t)stream, *rbm, op, nullptr, sigma, B, eloc_out, eloc_dtype);
+  return eloc_dispatch((cudaStream_t)stream, rbm, op, nullptr, sigma, B, eloc_out, eloc_dtype, path, workspace, "nk_eloc_ising_rbm");
 }
 
 int nk_eloc_localop_rbm(void *stream, const nk_rbm_t *rbm, const nk_localop_t *op, const int8_t *sigma, int64_t B, void *eloc_out,
-                        int32_t eloc_dtype) {
+                        int32_t eloc_dtype, int32_t path, void *workspace) {
   int rc = check_rbm(rbm, "nk_eloc_localop_rbm");
   if (rc) return rc;
   rc = check_localop(op, rbm->N, "nk_eloc_localop_rbm");
   if (rc) return rc;
   NK_CHECK_ARG(B >= 0 && (B == 0 || (sigma && eloc_out)), "nk_eloc_localop_rbm: bad batch / NULL buffer");
   NK_CHECK_ARG(eloc_dtype == NK_F32 || eloc_dtype == NK_F64, "nk_eloc_localop_rbm: bad eloc_dtype");
-  return eloc_generic((cudaStream_t)stream, *rbm, nullptr, op, sigma, B, eloc_out, eloc_dtype);
+  return eloc_dispatch((cudaStream_t)stream, rbm, nullptr, op, sigma, B, eloc_out, eloc_dtype, path, workspace, "nk_eloc_localop_rbm");
 }
 
 int nk_stats_partial(void *stream, const void *data, int32_t dtype, int64_t n_chains, int64_t L, int32_t phase, double shift,

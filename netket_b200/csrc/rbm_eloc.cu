@@ -38,6 +38,7 @@ struct ElocArgs {
   void *eloc_out;
   int32_t eloc_dtype;
   int32_t n_pad;
+  const int *run_if_flag;  // run iff NULL or *run_if_flag != 0 (hand-over from the product-form kernel)
 };
 
 template <typename T>
@@ -47,6 +48,7 @@ __global__ void __launch_bounds__(256) eloc_generic_kernel(const __grid_constant
   const RbmView<T> r = make_view<T>(p.rbm);
   T *theta = reinterpret_cast<T *>(smem_raw) + (size_t)warp * r.M;
   int8_t *sig = reinterpret_cast<int8_t *>(smem_raw + (size_t)warps * r.M * sizeof(T)) + (size_t)warp * p.n_pad;
+  if (p.run_if_flag != nullptr && *p.run_if_flag == 0) return;
   for (int64_t s = (int64_t)blockIdx.x * warps + warp; s < p.B; s += (int64_t)gridDim.x * warps) {
     for (int i = lane; i < r.N; i += 32) sig[i] = p.sigma[s * r.N + i];
     __syncwarp();
@@ -116,7 +118,7 @@ static int launch_eloc(cudaStream_t stream, ElocArgs a) {
 }
 
 int eloc_generic(cudaStream_t stream, const nk_rbm_t &rbm, const nk_ising_t *ising, const nk_localop_t *localop,
-                 const int8_t *sigma, int64_t B, void *eloc_out, int32_t eloc_dtype) {
+                 const int8_t *sigma, int64_t B, void *eloc_out, int32_t eloc_dtype, const int *run_if_flag) {
   if (B == 0) return NK_OK;
   ElocArgs a{};
   a.rbm = rbm;
@@ -127,6 +129,7 @@ int eloc_generic(cudaStream_t stream, const nk_rbm_t &rbm, const nk_ising_t *isi
   if (localop) a.localop = *localop;
   a.eloc_out = eloc_out;
   a.eloc_dtype = eloc_dtype;
+  a.run_if_flag = run_if_flag;
   return rbm.dtype == NK_F32 ? launch_eloc<float>(stream, a) : launch_eloc<double>(stream, a);
 }
 

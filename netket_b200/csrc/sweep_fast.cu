@@ -590,10 +590,4 @@ int sweep_fast(cudaStream_t stream, const SweepKernelArgs &a, const float *theta
   return NK_EUNSUPPORTED;
 }
 
-bool eloc_fast_supported(const nk_rbm_t &) { return false; }
-int eloc_fast_ising(cudaStream_t, const nk_rbm_t &, const nk_ising_t &, const int8_t *, int64_t, void *, int32_t) {
-  set_error("eloc_fast: not built");
-  return NK_EUNSUPPORTED;
-}
-
 }  // namespace nk

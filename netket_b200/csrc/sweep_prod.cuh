@@ -778,6 +778,7 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
         for (; k < kend; ++k) {
           const int thr = __shfl_sync(FULL, thr_l, k);
           const uint32_t w0 = __shfl_sync(FULL, w0_l, k);
+          if (s.eloc_only) continue;  // stand-alone local estimator: one empty "sweep", then the sample's E_loc
           if (since >= renorm) renormalise();
           if constexpr (RULE == NK_RULE_LOCAL) {
             const int site = (int)w0;
@@ -905,6 +906,7 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
         if (in_sweep == sweep_size) end_of_sweep();
       }
     }
+    if (s.eloc_only) continue;
     // ---- write the chain state back
 #pragma unroll
     for (int b = 0; b < 4; ++b) {

@@ -72,6 +72,7 @@ class MCState:
         self.sampler_state = sampler.init_state(model, variables, seed=self._sampler_seed)
         self._samples = None
         self._eloc_cache = {}
+        self._eloc_ws = None
         self._chain_length = None
         _, ws = world()
         if n_samples is not None and n_samples_per_rank is not None:
@@ -234,13 +235,21 @@ class MCState:
         out_dtype = torch.promote_types(_lib.torch_dtype(op.dtype), W.dtype)
         out = torch.empty((B,), dtype=out_dtype, device=dev)
         st = op._c_struct(dev)
+        ws = None
+        if path != _lib.NK_PATH_GENERIC:  # scratch of the product-form kernel (theta + tables), cached per size
+            nbytes = int(_lib.lib().nk_sweep_workspace_bytes(C.byref(rbm), B))
+            if nbytes > 0:
+                if self._eloc_ws is None or self._eloc_ws.numel() < nbytes or self._eloc_ws.device != dev:
+                    self._eloc_ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                ws = self._eloc_ws
+        wsp = _lib.ptr(ws) if ws is not None else None
         with torch.cuda.device(dev):
             if isinstance(op, IsingJax):
                 _lib.check(_lib.lib().nk_eloc_ising_rbm(_lib.stream_ptr(dev), C.byref(rbm), C.byref(st), _lib.ptr(s8), B,
-                                                        _lib.ptr(out), _lib.dtype_code(out_dtype), path))
+                                                        _lib.ptr(out), _lib.dtype_code(out_dtype), path, wsp))
             else:
                 _lib.check(_lib.lib().nk_eloc_localop_rbm(_lib.stream_ptr(dev), C.byref(rbm), C.byref(st), _lib.ptr(s8), B,
-                                                          _lib.ptr(out), _lib.dtype_code(out_dtype)))
+                                                          _lib.ptr(out), _lib.dtype_code(out_dtype), path, wsp))
         return out.reshape(shape)
 
     def local_estimators(self, op, *, chunk_size=None):

@@ -267,3 +267,53 @@ def test_prod_sampler_chi_square(cuda, dtype, rule, std):
     pv = sstats.chisquare(counts, p * counts.sum()).pvalue
     assert pv > 1e-3, pv
     assert 0.0 < st2.acceptance <= 1.0
+
+
+# ----------------------------------------------------------------------------------------- stand-alone local estimator
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("kind,L,n_dim,alpha,std", [("ising", 10, 2, 4, 0.01), ("ising", 10, 2, 4, 0.1), ("ising", 20, 1, 1, 0.3),
+                                                     ("heis", 22, 1, 2, 0.05), ("j1j2", 10, 2, 4, 0.03), ("heis", 4, 2, 2, 0.4)])
+def test_prod_standalone_eloc(cuda, dtype, kind, L, n_dim, alpha, std):
+    """nk_eloc_*_rbm on arbitrary configurations (not produced by a chain), product-form kernel vs oracle and vs the
+    theta-form kernel; leading batch dimensions are kept."""
+    nk = _nk()
+    if kind == "ising":
+        g = nk.graph.Hypercube(L, n_dim)
+        hi = nk.hilbert.Spin(0.5, g.n_nodes)
+        op = nk.operator.Ising(hi, g, h=3.0)
+        e, _ = ograph.hypercube_edges(L, n_dim)
+        conn = lambda x: oops.ising_conn_padded(x, e, 3.0, 1.0)  # noqa: E731
+        total_sz = None
+    else:
+        total_sz = 0
+        g, hi, op, tables = _heis(nk, L, n_dim, total_sz, [1.0, 0.5] if kind == "j1j2" else 1.0, None, 2 if kind == "j1j2" else 1)
+        conn = lambda x: oops.local_operator_conn_padded(x, tables)  # noqa: E731
+    N = g.n_nodes
+    (W, b, a), var = _params(N, alpha, dtype, std)
+    vs = nk.vqs.MCState(nk.sampler.MetropolisLocal(nk.hilbert.Spin(0.5, N), n_chains=16), nk.models.RBM(alpha=alpha, param_dtype=dtype),
+                        variables=var, n_samples=16, seed=1)
+    sig = ohilbert.random_state(9, 3 * 67, N, total_sz).reshape(3, 67, N)
+    out = vs._eloc_on_samples(op, torch.from_numpy(sig).cuda(), path=PROD)
+    assert tuple(out.shape) == (3, 67) and out.dtype == torch.float64
+    ref = oest.local_value_kernel(sig.reshape(-1, N), conn, *_f64(W, b, a)).reshape(3, 67)
+    tol = 1e-12 if dtype == np.float64 else 1e-5
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=tol, atol=tol * np.abs(ref).max())
+    gen = vs._eloc_on_samples(op, torch.from_numpy(sig).cuda(), path=1)
+    np.testing.assert_allclose(out.cpu().numpy(), gen.cpu().numpy(), rtol=2 * tol, atol=2 * tol * np.abs(ref).max())
+    auto = vs._eloc_on_samples(op, torch.from_numpy(sig).cuda(), path=0)
+    assert np.array_equal(auto.cpu().numpy(), out.cpu().numpy())
+
+
+def test_prod_standalone_eloc_hands_over_for_large_weights(cuda):
+    nk = _nk()
+    g = nk.graph.Hypercube(4, 2)
+    hi = nk.hilbert.Spin(0.5, 16)
+    op = nk.operator.Ising(hi, g, h=1.0)
+    (W, b, a), var = _params(16, 16, np.float64, 1.5)
+    vs = nk.vqs.MCState(nk.sampler.MetropolisLocal(hi, n_chains=16), nk.models.RBM(alpha=16), variables=var, n_samples=16, seed=1)
+    sig = torch.from_numpy(ohilbert.random_state(2, 50, 16)).cuda()
+    assert np.array_equal(vs._eloc_on_samples(op, sig, path=0).cpu().numpy(), vs._eloc_on_samples(op, sig, path=1).cpu().numpy())
+    with pytest.raises(nk.NkError):
+        nk.vqs.MCState(nk.sampler.MetropolisLocal(nk.hilbert.Spin(0.5, 130), n_chains=16), nk.models.RBM(alpha=1),
+                       n_samples=16, seed=1)._eloc_on_samples(nk.operator.Ising(nk.hilbert.Spin(0.5, 130), nk.graph.Hypercube(130, 1), h=1.0),
+                                                              torch.ones((4, 130), dtype=torch.int8, device="cuda"), path=PROD)
