@@ -213,22 +213,38 @@ def measure(nk, torch, dist, rank, ws, device, dtype, steps, warmup):
         _lib.check(L.nk_theta_gemm(_lib.stream_ptr(device), C.byref(rbm), _lib.ptr(st0.σ), CHAINS_PER_GPU, _lib.ptr(theta),
                                    _lib.ptr(scratch)))
 
-    ms_theta = timed_steps(torch, dist, 1, theta_only, 5, 2) / 5 if dtype == "float32" else 0.0
+    ms_theta = timed_steps(torch, dist, 1, theta_only, 5, 2) / 5
     ms_kernel = ms_sweep_call - ms_theta
     alg_bytes = CHAINS_PER_GPU * CHAIN_LENGTH * bytes_per_sample(esz)
     achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
     res = C.c_double()
-    which, bound = (0, "smem") if dtype == "float32" else (1, "l2")
-    _lib.check(L.nk_microbench(which, C.byref(res)))
+    _lib.check(L.nk_microbench(0, C.byref(res)))
     peak = float(res.value)
-    roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": "sweep_fast_kernel<3,1> (fused sweep + E_loc)" if dtype == "float32" else "sweep_generic_kernel<double>",
-                "kernel_ms": ms_kernel, "theta_kernel_ms": ms_theta,
+    kernel = ("sweep_fast_kernel<3,1> (fused sweep + E_loc, fp32 LocalRule specialisation)" if dtype == "float32"
+              else "sweep_prod_kernel<double,6,1,LocalRule> (fused sweep + E_loc; 66 of 100 table rows resident in shared memory, "
+                   "the others read through L2)")
+    roofline = {"bound": "smem", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": kernel, "kernel_ms": ms_kernel, "theta_kernel_ms": ms_theta,
                 "algorithmic_bytes_per_sample": bytes_per_sample(esz),
-                "peak_source": f"measured in this run by nk_microbench({which}) ({'LDS.128 shared-memory' if which == 0 else 'L2'} read "
-                               "bandwidth, all SMs); MEASURED_PEAKS.json holds no on-chip figure (its HBM copy number does not bound "
-                               "this path: HBM traffic is ~120 B/sample)",
+                "peak_source": "measured in this run by nk_microbench(0) (LDS.128 shared-memory read bandwidth, all SMs); "
+                               "MEASURED_PEAKS.json holds no on-chip figure (its HBM copy number does not bound this path: HBM "
+                               "traffic is ~120 B/sample)",
                 "method": "CUDA events on the launching stream around nk_sweep, minus the separately timed theta kernel"}
+    if dtype == "float64":
+        # competing bounds of the fp64 kernel, measured in the same run: the FP64 pipe (one DFMA + one DMUL per table element
+        # and row operation, one more DMUL per element of an accepted move) and the L2 reads of the non-resident rows
+        _lib.check(L.nk_microbench(4, C.byref(res)))
+        dp_peak_inst = float(res.value) / 2.0  # G lane-instructions/s (the microbenchmark counts 2 flop per DFMA)
+        acc = float(vs.sampler_state.acceptance)
+        dp_per_sample = N_SITES * N_HIDDEN * (2.0 + acc + 2.0)
+        dp_ach = CHAINS_PER_GPU * CHAIN_LENGTH * dp_per_sample / (ms_kernel * 1e-3) / 1e9
+        _lib.check(L.nk_microbench(1, C.byref(res)))
+        l2_peak = float(res.value)
+        l2_bytes = (1.0 - 66.0 / 100.0) * bytes_per_sample(esz)
+        roofline["competing"] = {
+            "fp64_pipe": {"achieved": dp_ach, "peak": dp_peak_inst, "unit": "G lane-instructions/s", "frac": dp_ach / dp_peak_inst},
+            "l2": {"achieved": CHAINS_PER_GPU * CHAIN_LENGTH * l2_bytes / (ms_kernel * 1e-3) / 1e9, "peak": l2_peak, "unit": "GB/s",
+                   "frac": CHAINS_PER_GPU * CHAIN_LENGTH * l2_bytes / (ms_kernel * 1e-3) / 1e9 / l2_peak}}
     return {"value": value, "ms_per_step": ms / steps, "launches": launches, "roofline": roofline, "stats": result["stats"],
             "acceptance": vs.sampler_state.acceptance, "params": (W, b, a)}
 

@@ -186,8 +186,9 @@ int nk_sweep(void *stream, const nk_rbm_t *rbm, nk_chains_t *ch, const nk_sweep_
   const bool fast_ok = a->path != NK_PATH_PROD && sweep_fast_supported(k) && have_ws;
   const bool prod_ok = !fast_ok && sweep_prod_supported(k) && have_ws;
   if ((a->path == NK_PATH_FAST || a->path == NK_PATH_PROD) && !fast_ok && !prod_ok) {
-    set_error("nk_sweep: no product-form kernel for this configuration (needs N<=128, M<=512, at most 2048 exchange clusters "
-              "with at most 32 per site, 1- and 2-site operator terms, and a workspace of nk_sweep_workspace_bytes())");
+    set_error("nk_sweep: no product-form kernel for this configuration (needs N<=1024, M<=512 per warp with at most 16 warps "
+              "per chain (LocalRule) or M<=512 (ExchangeRule), at most 2048 exchange clusters with at most 32 per site, 1- and "
+              "2-site operator terms, and a workspace of nk_sweep_workspace_bytes())");
     return NK_EUNSUPPORTED;
   }
   if (a->path != NK_PATH_GENERIC && (fast_ok || prod_ok)) {
@@ -265,7 +266,7 @@ static int eloc_dispatch(cudaStream_t st, const nk_rbm_t *rbm, const nk_ising_t 
   k.eloc_only = 1;
   const bool prod_ok = workspace != nullptr && sweep_prod_supported(k);
   if ((path == NK_PATH_FAST || path == NK_PATH_PROD) && !prod_ok) {
-    set_error("%s: no product-form kernel for this configuration (needs N<=128, M<=512, 1- and 2-site operator terms and a "
+    set_error("%s: no product-form kernel for this configuration (needs N<=1024, M<=8192, 1- and 2-site operator terms and a "
               "workspace of nk_sweep_workspace_bytes())", who);
     return NK_EUNSUPPORTED;
   }

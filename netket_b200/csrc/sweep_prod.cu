@@ -16,6 +16,7 @@ using namespace prod;
 
 template <typename T>
 __global__ void __launch_bounds__(128) prod_prep_rows(const __grid_constant__ ProdArgs p, int MP) {
+  // row layout: kw segments (one per cooperating warp) of MP elements; segment k holds hidden units [k mw, (k+1) mw)
   typedef typename VecOf<T>::Rc Rc;
   __shared__ double red[3][4];
   const int i = blockIdx.x, N = p.s.rbm.N, M = p.s.rbm.M;
@@ -23,9 +24,11 @@ __global__ void __launch_bounds__(128) prod_prep_rows(const __grid_constant__ Pr
   const T *W = reinterpret_cast<const T *>(p.s.rbm.W) + (size_t)i * M;
   T *row = reinterpret_cast<T *>(const_cast<unsigned char *>(p.gtab) + (size_t)i * p.L.row_bytes);
   double rs = 0.0, ra = 0.0, wm = 0.0;
-  for (int j = threadIdx.x; j < MP; j += blockDim.x) {
+  const int kw = p.L.kw, mw = p.L.mw;
+  for (int pos = threadIdx.x; pos < kw * MP; pos += blockDim.x) {
+    const int seg = pos / MP, t = pos - seg * MP, j = seg * mw + t;
     T g = T(1);  // padding: leaves every product unchanged
-    if (j < M) {
+    if (t < mw && j < M) {
       const T w = W[j];
       g = Math<T>::exp(T(-4) * w);
       rs += (double)w;
@@ -33,7 +36,7 @@ __global__ void __launch_bounds__(128) prod_prep_rows(const __grid_constant__ Pr
       wm = fmax(wm, fabs((double)w));
       if (!(fabs((double)w) < 1.0e30)) wm = 1.0e300;  // NaN / Inf
     }
-    row[j] = g;
+    row[pos] = g;
   }
 #pragma unroll
   for (int m = 16; m > 0; m >>= 1) {
@@ -77,19 +80,19 @@ __global__ void __launch_bounds__(128) prod_prep_rows(const __grid_constant__ Pr
 
 template <typename T>
 __global__ void __launch_bounds__(256) prod_prep_tables(const __grid_constant__ ProdArgs p, int NE_pad) {
-  __shared__ int deg[128];
+  __shared__ int deg[1024];
   __shared__ int bad;
   const SweepKernelArgs &s = p.s;
   const ProdLayout &L = p.L;
   unsigned char *aux = const_cast<unsigned char *>(p.aux);
   const int N = s.rbm.N, tid = threadIdx.x, nt = blockDim.x;
   if (tid == 0) bad = 0;
-  for (int i = tid; i < 128; i += nt) deg[i] = 0;
+  for (int i = tid; i < 1024; i += nt) deg[i] = 0;
   __syncthreads();
   // ---- ExchangeRule tables
   if (s.rule == NK_RULE_EXCHANGE) {
     const int C = s.n_clusters;
-    uint8_t *cl = aux + L.cl_off;
+    uint16_t *cl = reinterpret_cast<uint16_t *>(aux + L.cl_off);
     uint32_t *adj = reinterpret_cast<uint32_t *>(aux + L.adj_off);
     int *lg = reinterpret_cast<int *>(aux + L.lg_off);
     for (int c = tid; c < C; c += nt) {
@@ -98,8 +101,8 @@ __global__ void __launch_bounds__(256) prod_prep_tables(const __grid_constant__ 
         bad = 1;
         continue;
       }
-      cl[2 * c] = (uint8_t)i;
-      cl[2 * c + 1] = (uint8_t)j;
+      cl[2 * c] = (uint16_t)i;
+      cl[2 * c + 1] = (uint16_t)j;
       const int a = atomicAdd(&deg[i], 1), b = atomicAdd(&deg[j], 1);
       if (a < PROD_ADJ_MAX) adj[i * PROD_ADJ_MAX + a] = (uint32_t)c | ((uint32_t)j << 16);
       if (b < PROD_ADJ_MAX) adj[j * PROD_ADJ_MAX + b] = (uint32_t)c | ((uint32_t)i << 16);
@@ -114,11 +117,11 @@ __global__ void __launch_bounds__(256) prod_prep_tables(const __grid_constant__ 
   }
   // ---- Ising edges
   if (s.eloc_kind == 1) {
-    uint8_t *edges = aux + L.edges_off;
+    uint16_t *edges = reinterpret_cast<uint16_t *>(aux + L.edges_off);
     for (int e = tid; e < 2 * s.ising.n_edges; e += nt) {
       const int v = s.ising.edges[e];
       if (v < 0 || v >= N) bad = 1;
-      edges[e] = (uint8_t)v;
+      edges[e] = (uint16_t)v;
     }
   }
   // ---- LocalOperator: compact tables
@@ -126,15 +129,15 @@ __global__ void __launch_bounds__(256) prod_prep_tables(const __grid_constant__ 
     for (int gi = 0; gi < s.localop.n_groups; ++gi) {
       const nk_localop_group_t &G = s.localop.groups[gi];
       const int rows = 1 << G.n_sites, ncm = G.ncmax;
-      uint8_t *sites = aux + L.lop_sites_off[gi];
+      uint16_t *sites = reinterpret_cast<uint16_t *>(aux + L.lop_sites_off[gi]);
       T *dg = reinterpret_cast<T *>(aux + L.lop_diag_off[gi]);
       T *ml = reinterpret_cast<T *>(aux + L.lop_mel_off[gi]);
       uint8_t *cd = aux + L.lop_code_off[gi];
       for (int o = tid; o < G.n_ops; o += nt) {
         const int s0 = G.acting_on[o * G.n_sites], s1 = G.n_sites == 2 ? G.acting_on[o * G.n_sites + 1] : s0;
         if (s0 < 0 || s1 < 0 || s0 >= N || s1 >= N || (G.n_sites == 2 && s0 == s1)) bad = 1;
-        sites[2 * o] = (uint8_t)s0;
-        sites[2 * o + 1] = (uint8_t)s1;
+        sites[2 * o] = (uint16_t)s0;
+        sites[2 * o + 1] = (uint16_t)s1;
       }
       for (int e = tid; e < G.n_ops * rows; e += nt) dg[e] = (T)G.diag_mels[e];
       for (int e = tid; e < G.n_ops * rows * ncm; e += nt) {
@@ -173,13 +176,15 @@ __global__ void __launch_bounds__(256) prod_prep_tables(const __grid_constant__ 
 
 // ------------------------------------------------------------------------------------------ host side
 struct ProdShape {
-  int nfull, tail, ne_pad, row_bytes, mp;
+  int nfull, tail, ne_pad, seg_bytes, mp;  // per-warp segment
+  int kw, mw;                              // warps per chain, hidden units per warp
 };
 
-static bool prod_shape(int M, int dtype, ProdShape *ps) {
+// shape of one warp's segment holding `m` hidden units
+static bool seg_shape(int m, int dtype, ProdShape *ps) {
   const int esz = dtype == NK_F32 ? 4 : 8;
   const int chunk = 512 / esz;  // elements per 512-byte chunk
-  int nfull = M / chunk, rem = M % chunk, tail = 0;
+  int nfull = m / chunk, rem = m % chunk, tail = 0;
   if (rem == 0)
     tail = 0;
   else if (rem <= 32)
@@ -191,29 +196,60 @@ static bool prod_shape(int M, int dtype, ProdShape *ps) {
     tail = 0;
   }
   const int max_full = esz == 4 ? 4 : 8;
-  if (M < 1 || nfull > max_full || (nfull == max_full && tail != 0)) return false;
+  if (m < 1 || nfull > max_full || (nfull == max_full && tail != 0)) return false;
   ps->nfull = nfull;
   ps->tail = tail;
   const int ne = (16 / esz) * nfull + tail;
   ps->ne_pad = esz == 4 ? 2 * ((ne + 1) / 2) : ne;
   ps->mp = 32 * (16 / esz) * nfull + 32 * tail;
-  ps->row_bytes = ps->mp * esz;
+  ps->seg_bytes = ps->mp * esz;
   return true;
 }
-
-static inline int align16(int x) { return (x + 15) & ~15; }
 
 static int prod_warps(int dtype, int rule) {
   return dtype == NK_F32 ? (rule == NK_RULE_LOCAL ? ProdWarps<float, NK_RULE_LOCAL>::value : ProdWarps<float, NK_RULE_EXCHANGE>::value)
                          : (rule == NK_RULE_LOCAL ? ProdWarps<double, NK_RULE_LOCAL>::value : ProdWarps<double, NK_RULE_EXCHANGE>::value);
 }
 
+// M <= 512: one warp per chain.  Larger hidden layers (LocalRule): kw warps per chain, chosen to waste the least padding
+// among the instantiated segment shapes (at least half-full segments), then the fewest warps.
+static bool prod_shape(int M, int dtype, int rule, ProdShape *ps) {
+  if (seg_shape(M, dtype, ps)) {
+    ps->kw = 1;
+    ps->mw = M;
+    return true;
+  }
+  if (rule != NK_RULE_LOCAL) return false;
+  const int warps = prod_warps(dtype, rule);
+  const int min_full = dtype == NK_F32 ? 2 : 4;
+  long best = -1;
+  for (int kw = 2; kw <= 16 && kw <= warps; ++kw) {
+    ProdShape c;
+    const int mw = (M + kw - 1) / kw;
+    if (!seg_shape(mw, dtype, &c) || c.nfull < min_full) continue;
+    const long cost = (long)kw * c.mp * 64 + kw;
+    if (best < 0 || cost < best) {
+      best = cost;
+      *ps = c;
+      ps->kw = kw;
+      ps->mw = mw;
+    }
+  }
+  return best >= 0;
+}
+
+static inline int align16(int x) { return (x + 15) & ~15; }
+
 static bool prod_layout(const SweepKernelArgs &a, const ProdShape &ps, ProdLayout *L) {
   const int esz = a.rbm.dtype == NK_F32 ? 4 : 8;
   const int N = a.rbm.N;
   memset(L, 0, sizeof(*L));
-  L->row_bytes = ps.row_bytes;
-  L->warps = prod_warps(a.rbm.dtype, a.rule);
+  L->seg_bytes = ps.seg_bytes;
+  L->row_bytes = ps.kw * ps.seg_bytes;
+  L->kw = ps.kw;
+  L->mw = ps.mw;
+  const int max_warps = prod_warps(a.rbm.dtype, a.rule);
+  L->warps = (max_warps / ps.kw) * ps.kw;
   int off = 0;
   L->rc_off = off;
   L->rc_stride = esz == 4 ? (int)sizeof(RcF) : (int)sizeof(RcD);
@@ -223,7 +259,7 @@ static bool prod_layout(const SweepKernelArgs &a, const ProdShape &ps, ProdLayou
     L->lg_off = off;
     off = align16(off + (C + 2) * 4);
     L->cl_off = off;
-    off = align16(off + 2 * C);
+    off = align16(off + 4 * C);
     L->adjdeg_off = off;
     off = align16(off + N);
     L->adj_off = off;
@@ -231,7 +267,7 @@ static bool prod_layout(const SweepKernelArgs &a, const ProdShape &ps, ProdLayou
   }
   if (a.eloc_kind == 1) {
     L->edges_off = off;
-    off = align16(off + 2 * a.ising.n_edges);
+    off = align16(off + 4 * a.ising.n_edges);
   }
   if (a.eloc_kind == 2) {
     for (int gi = 0; gi < a.localop.n_groups; ++gi) {
@@ -240,7 +276,7 @@ static bool prod_layout(const SweepKernelArgs &a, const ProdShape &ps, ProdLayou
       const int64_t total = (int64_t)G.n_ops * rows * (G.ncmax + 1) * (esz + 1);
       if (total > PROD_AUX_MAX) return false;
       L->lop_sites_off[gi] = off;
-      off = align16(off + 2 * G.n_ops);
+      off = align16(off + 4 * G.n_ops);
       L->lop_diag_off[gi] = off;
       off = align16(off + (int)(G.n_ops * rows) * esz);
       L->lop_mel_off[gi] = off;
@@ -251,17 +287,35 @@ static bool prod_layout(const SweepKernelArgs &a, const ProdShape &ps, ProdLayou
   }
   if (off > PROD_AUX_MAX) return false;
   L->aux_bytes = off;
-  const int hop_bytes = a.rule == NK_RULE_EXCHANGE ? L->warps * PROD_HOP_WORDS * 4 : 0;
-  const int fixed = L->aux_bytes + hop_bytes + 16;
-  const int budget = 227 * 1024 - fixed;
-  if (budget < 0) return false;
-  int n_res = budget / ps.row_bytes;
-  if (n_res > N) n_res = N;
-  if (esz == 4 && n_res < N) return false;  // fp32 kernels read the table with explicit shared-memory loads only
+  const int hop_bytes = a.rule == NK_RULE_EXCHANGE ? max_warps * PROD_HOP_WORDS * 4 : 0;
+  // MULTI kernels (generic-address rows, cross-warp slots): several warps per chain, or an fp32 table that does not fit
+  // shared memory (the one-warp fp32 kernels read the table with explicit shared-memory loads only)
+  int multi = ps.kw > 1 ? 1 : 0;
+  int n_res = 0, xs_bytes = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    if (multi) {  // one named barrier (ids 1..15) per chain slot of the CTA
+      int groups = max_warps / ps.kw;
+      if (groups > 15) groups = 15;
+      L->warps = groups * ps.kw;
+    }
+    xs_bytes = multi ? (L->warps / ps.kw) * 2 * ps.kw * 256 : 0;
+    const int budget = 227 * 1024 - (L->aux_bytes + hop_bytes + xs_bytes + 16);
+    if (budget < 0) return false;
+    n_res = budget / L->row_bytes;
+    if (n_res > N) n_res = N;
+    if (esz == 4 && !multi && n_res < N) {
+      if (a.rule != NK_RULE_LOCAL || ps.nfull < 2) return false;
+      multi = 1;
+      continue;
+    }
+    break;
+  }
+  L->multi = multi;
   L->n_res = n_res;
-  L->g_bytes = n_res * ps.row_bytes;
+  L->g_bytes = n_res * L->row_bytes;
   L->hop_off = L->g_bytes + L->aux_bytes;
-  L->bar_off = L->hop_off + hop_bytes;
+  L->xs_off = L->hop_off + hop_bytes;
+  L->bar_off = L->xs_off + xs_bytes;
   L->smem_bytes = L->bar_off + 16;
   return true;
 }
@@ -269,7 +323,7 @@ static bool prod_layout(const SweepKernelArgs &a, const ProdShape &ps, ProdLayou
 bool sweep_prod_supported(const SweepKernelArgs &a) {
   ProdShape ps;
   ProdLayout L;
-  if (a.rbm.N > 128 || !prod_shape(a.rbm.M, a.rbm.dtype, &ps)) return false;
+  if (a.rbm.N > 1024 || !prod_shape(a.rbm.M, a.rbm.dtype, a.rule, &ps)) return false;
   if (a.rule == NK_RULE_EXCHANGE && (a.n_clusters < 1 || a.n_clusters > 32 * PROD_HOP_WORDS)) return false;
   if (a.eloc_kind == 1 && a.ising.n_edges > 8192) return false;
   if (a.B >= (1ll << 31) || (int64_t)(a.n_discard + a.chain_length) * a.sweep_size >= (1ll << 31)) return false;  // 32-bit counters
@@ -279,27 +333,29 @@ bool sweep_prod_supported(const SweepKernelArgs &a) {
 // bytes of workspace behind theta and the flags: the G table and the aux blob
 size_t sweep_prod_workspace_bytes(const nk_rbm_t &rbm) {
   ProdShape ps;
-  if (rbm.N > 128 || !prod_shape(rbm.M, rbm.dtype, &ps)) return 0;
-  return (((size_t)rbm.N * ps.row_bytes + 255) & ~(size_t)255) + PROD_AUX_MAX;
+  if (rbm.N > 1024 || !prod_shape(rbm.M, rbm.dtype, NK_RULE_LOCAL, &ps)) return 0;
+  return (((size_t)rbm.N * ps.kw * ps.seg_bytes + 255) & ~(size_t)255) + PROD_AUX_MAX;
 }
 
 int sweep_prod(cudaStream_t stream, const SweepKernelArgs &a, const void *theta_ws, int *flags, void *tables_ws) {
   ProdShape ps;
   ProdArgs pa{};
-  if (!prod_shape(a.rbm.M, a.rbm.dtype, &ps) || !prod_layout(a, ps, &pa.L)) {
+  if (!prod_shape(a.rbm.M, a.rbm.dtype, a.rule, &ps) || !prod_layout(a, ps, &pa.L)) {
     set_error("sweep_prod: unsupported configuration");
     return NK_EUNSUPPORTED;
   }
   pa.s = a;
   pa.gtab = reinterpret_cast<const unsigned char *>(tables_ws);
-  pa.aux = pa.gtab + (((size_t)a.rbm.N * ps.row_bytes + 255) & ~(size_t)255);
+  pa.aux = pa.gtab + (((size_t)a.rbm.N * pa.L.row_bytes + 255) & ~(size_t)255);
   pa.theta = theta_ws;
   pa.flags = flags;
+  const bool multi = pa.L.multi != 0;
   if (a.rbm.dtype == NK_F32) {
     prod_prep_rows<float><<<a.rbm.N, 128, 0, stream>>>(pa, ps.mp);
     NK_LAUNCH_OK();
     prod_prep_tables<float><<<1, 256, 0, stream>>>(pa, ps.ne_pad);
     NK_LAUNCH_OK();
+    if (multi) return launch_prod_f32_local_multi(stream, pa, ps.nfull, ps.tail);
     return a.rule == NK_RULE_LOCAL ? launch_prod_f32_local(stream, pa, ps.nfull, ps.tail)
                                    : launch_prod_f32_exchange(stream, pa, ps.nfull, ps.tail);
   }
@@ -307,6 +363,7 @@ int sweep_prod(cudaStream_t stream, const SweepKernelArgs &a, const void *theta_
   NK_LAUNCH_OK();
   prod_prep_tables<double><<<1, 256, 0, stream>>>(pa, ps.ne_pad);
   NK_LAUNCH_OK();
+  if (multi) return launch_prod_f64_local_multi(stream, pa, ps.nfull, ps.tail);
   return a.rule == NK_RULE_LOCAL ? launch_prod_f64_local(stream, pa, ps.nfull, ps.tail)
                                  : launch_prod_f64_exchange(stream, pa, ps.nfull, ps.tail);
 }

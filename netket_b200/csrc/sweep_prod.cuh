@@ -41,12 +41,16 @@ struct ProdLayout {
   int row_bytes, n_res, g_bytes, aux_bytes;
   int rc_off, rc_stride;           // per-site constants (RcF / RcD)
   int lg_off;                      // exchange: fix(log2(n) / machine_pow), n = 0..C
-  int cl_off;                      // exchange: clusters as uint8 pairs
+  int cl_off;                      // exchange: clusters as uint16 pairs
   int adjdeg_off, adj_off;         // exchange: clusters per site: degree (uint8), entries (cluster | partner << 16)
-  int edges_off;                   // Ising: edges as uint8 pairs
+  int edges_off;                   // Ising: edges as uint16 pairs
   int lop_sites_off[2], lop_diag_off[2], lop_mel_off[2], lop_code_off[2];  // LocalOperator, compact tables
   int hop_off, bar_off, smem_bytes;
-  int warps;
+  int warps;            // warps per CTA actually launched (groups * kw)
+  int kw, mw;           // warps cooperating on one chain, hidden units owned by each of them (kw == 1: mw == M)
+  int seg_bytes;        // bytes of one warp's segment of a table row (row_bytes = kw * seg_bytes)
+  int xs_off;           // MULTI kernels: cross-warp exchange slots, 2 * kw * 32 * 8 bytes per group
+  int multi;            // 1: the MULTI instantiation is launched
 };
 
 struct ProdArgs {
@@ -294,10 +298,13 @@ static __device__ __noinline__ double rcp_sum(double a, double b) { return 1.0 /
 
 // fp64 only, rare: the decision of a proposal whose fixed-point test fell inside the approximation's error band.
 //   accept  <=>  u < exp(machine_pow * (cst + sum_lanes log(Pprop / Pcur)) + corr)      (metropolis.py:444-450)
-static __device__ __noinline__ bool exact_accept(double Pprop, double Pcur, double cst, double u, double pw, double corr) {
+static __device__ __noinline__ double exact_logratio(double Pprop, double Pcur) {
   double d = log(Pprop / Pcur);
 #pragma unroll
   for (int m = 16; m > 0; m >>= 1) d += __shfl_xor_sync(0xffffffffu, d, m);
+  return d;
+}
+static __device__ __noinline__ bool exact_decide(double d, double cst, double u, double pw, double corr) {
   return u < exp(pw * (cst + d) + corr);
 }
 
@@ -324,8 +331,10 @@ __device__ __forceinline__ T bfly(T (&v)[NB], int lane) {
 }
 
 // candidate descriptor (one connected configuration): sites, which of them change and to which sign
-//   bits 0-7 s0, 8-15 s1, 16 chg0, 17 chg1, 18 pos0 (sigma'_{s0} = +1), 19 pos1, 31 valid
-constexpr uint32_t CD_CHG0 = 1u << 16, CD_CHG1 = 1u << 17, CD_POS0 = 1u << 18, CD_POS1 = 1u << 19, CD_VALID = 1u << 31;
+//   bits 0-9 s0, 10-19 s1, 20 chg0, 21 chg1, 22 pos0 (sigma'_{s0} = +1), 23 pos1, 31 valid
+constexpr uint32_t CD_CHG0 = 1u << 20, CD_CHG1 = 1u << 21, CD_POS0 = 1u << 22, CD_POS1 = 1u << 23, CD_VALID = 1u << 31;
+constexpr int CD_S1_SHIFT = 10;
+constexpr uint32_t CD_SITE_MASK = 1023u;
 
 #ifndef NK_PROD_WARPS_F32L
 #define NK_PROD_WARPS_F32L 20
@@ -349,15 +358,17 @@ struct ProdWarps {
 }  // namespace prod
 
 // ============================================================================================== the kernel
-template <typename T, int NFULL, int TAIL, int RULE>
+// MULTI: kw > 1 warps cooperate on one chain (hidden units split between them; per-proposal partial sums are combined
+// through shared memory and a named barrier) and the table rows are read with generic-address loads (mostly through L2).
+template <typename T, int NFULL, int TAIL, int RULE, bool MULTI>
 __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep_prod_kernel(const __grid_constant__ ProdArgs p) {
   using namespace prod;
   typedef LaneMap<T, NFULL, TAIL> LM;
   typedef typename LM::V V;
   typedef typename VecOf<T>::Rc Rc;
   constexpr int NV = LM::NV, NE = LM::NE, ROW_BYTES = LM::ROW_BYTES;
-  constexpr int WARPS = ProdWarps<T, RULE>::value;
   constexpr bool F64 = sizeof(T) == 8;
+  constexpr bool GENERIC_ROWS = F64 || MULTI;  // generic-address row loads (rows partly or wholly outside shared memory)
   constexpr uint32_t FULL = 0xffffffffu;
   extern __shared__ __align__(128) unsigned char smem[];
   const SweepKernelArgs &s = p.s;
@@ -367,6 +378,12 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
   const int N = s.rbm.N, M = s.rbm.M;
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(FULL, tid >> 5, 0);
+  const int KW = MULTI ? L.kw : 1;                 // warps per chain
+  const int grp = MULTI ? warp / KW : warp;        // chain slot of this warp inside the CTA
+  const int wk = MULTI ? warp - grp * KW : 0;      // which part of the hidden layer this warp owns
+  const int groups = MULTI ? L.warps / KW : L.warps;
+  const int MW = MULTI ? L.mw : M;                 // hidden units of this warp: [wk * MW, min((wk + 1) * MW, M))
+  const int nbw = (N + 31) >> 5;                   // sigma bit words (bits per lane)
   unsigned char *aux = smem + L.g_bytes;
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L.bar_off);
   uint32_t *hopw = reinterpret_cast<uint32_t *>(smem + L.hop_off) + warp * PROD_HOP_WORDS;
@@ -388,10 +405,10 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
 
   const Rc *rctab = reinterpret_cast<const Rc *>(aux + L.rc_off);
   const int *lgtab = reinterpret_cast<const int *>(aux + L.lg_off);
-  const uint8_t *cl = aux + L.cl_off;
+  const uint16_t *cl = reinterpret_cast<const uint16_t *>(aux + L.cl_off);
   const uint8_t *adjdeg = aux + L.adjdeg_off;
   const uint32_t *adj = reinterpret_cast<const uint32_t *>(aux + L.adj_off);
-  const uint8_t *edges = aux + L.edges_off;
+  const uint16_t *edges = reinterpret_cast<const uint16_t *>(aux + L.edges_off);
   const int E = s.eloc_kind == 1 ? s.ising.n_edges : 0;
   const int C = RULE == NK_RULE_EXCHANGE ? s.n_clusters : 0;
 
@@ -399,27 +416,51 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
   const T pw = (T)s.machine_pow;
   const T inv_pw = pw > T(0) ? T(1) / pw : T(0);
   const T LN2 = (T)0.69314718055994530942, LOG2E = (T)1.4426950408889634;
-  // rows: the first n_res live in shared memory, the others are read from the global table (through L2)
-  // (fp32 kernels are only launched when the whole table is resident: explicit LDS; fp64 uses generic addresses)
+  // rows: the first n_res live in shared memory, the others are read from the global table (through L2).
+  // fp32 single-warp kernels are only launched when the whole table is resident (explicit LDS); the others use
+  // generic addresses so that one instruction stream serves both kinds of row.
   uint32_t lane_row = s32(smem) + 16u * lane;
   uint32_t lane_tail = s32(smem) + (uint32_t)LM::TAIL_OFF + (uint32_t)LM::TAIL_LANE * lane;
-  const unsigned char *sbase = smem;    // generic address of the resident rows
-  const unsigned char *gbase = p.gtab;
+  const unsigned char *sbase = smem + (size_t)wk * ROW_BYTES;    // generic address of the resident rows (this warp's segment)
+  const unsigned char *gbase = p.gtab + (size_t)wk * ROW_BYTES;
+  const int row_stride = L.row_bytes;
   int n_res = L.n_res;
   int sweep_size = s.sweep_size;
   asm volatile("" : "+r"(lane_row), "+r"(lane_tail), "+r"(n_res), "+r"(sweep_size));
 
   auto fetch = [&](int site, V(&g)[NV]) {
-    if constexpr (!F64) {
+    if constexpr (!GENERIC_ROWS) {
       const uint32_t o = (uint32_t)site * (uint32_t)ROW_BYTES;
       load_row_s<NFULL, TAIL>(lane_row + o, lane_tail + o, g);
     } else {
-      const unsigned char *row = (site < n_res ? sbase : gbase) + (size_t)site * ROW_BYTES;
+      const unsigned char *row = (site < n_res ? sbase : gbase) + (size_t)site * row_stride;
       load_row_p<NFULL, TAIL>(row + 16 * lane, row + LM::TAIL_OFF + LM::TAIL_LANE * lane, g);
     }
   };
 
-  for (int chain = blockIdx.x * WARPS + warp; chain < (int)s.B; chain += gridDim.x * WARPS) {
+  // cross-warp combination (MULTI): every lane contributes one value and gets the combination over the KW warps of its
+  // chain.  Two slot buffers alternate, so one named barrier per call suffices (a warp can only come back to the same
+  // buffer after the next call's barrier, i.e. after every warp has read this call's slots).
+  unsigned char *xs_group = smem + L.xs_off + (size_t)grp * (2 * KW * 256);
+  int xphase = 0;
+  auto gcomb = [&](auto v, auto op) {
+    typedef decltype(v) U;
+    if constexpr (!MULTI) {
+      return v;
+    } else {
+      U *buf = reinterpret_cast<U *>(xs_group + xphase * (KW * 256));
+      xphase ^= 1;
+      buf[wk * 32 + lane] = v;
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(KW * 32) : "memory");
+      U r = buf[lane];
+      for (int k = 1; k < KW; ++k) r = op(r, buf[k * 32 + lane]);
+      return r;
+    }
+  };
+  auto op_add = [](auto a, auto b) { return a + b; };
+  auto op_mul = [](auto a, auto b) { return a * b; };
+
+  for (int chain = blockIdx.x * groups + grp; chain < (int)s.B; chain += gridDim.x * groups) {
     V A[NV], Bv[NV];
     // sigma, lane-distributed: bit b of lane l is set iff sigma of site 32 b + l is -1
     uint32_t mybits = 0;
@@ -427,39 +468,25 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
     uint32_t nacc = 0;
     {
       const int8_t *sg = s.sigma + (size_t)chain * N;
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
+      for (int b = 0; b < nbw; ++b) {
         const int idx = 32 * b + lane;
         if (idx < N && sg[idx] < 0) mybits |= 1u << b;
       }
     }
-    // spin bit of an arbitrary (warp-uniform or not) site: one shuffle
+    // spin bit of any site (the site may differ between lanes; all lanes must call): one shuffle
     auto sbit = [&](int site) -> uint32_t { return (__shfl_sync(FULL, mybits, site & 31) >> (site >> 5)) & 1u; };
     auto stoggle = [&](int site) {
       if (lane == (site & 31)) mybits ^= 1u << (site >> 5);
     };
     auto ownbit = [&](int b) -> uint32_t { return (mybits >> b) & 1u; };  // site 32 b + lane
-    // sigma as four bit words replicated in every lane (for lane-parallel table walks)
-    struct Words {
-      uint32_t w0, w1, w2, w3;
-      __device__ __forceinline__ uint32_t bit(int site) const { return (sel4(w0, w1, w2, w3, site >> 5) >> (site & 31)) & 1u; }
-    };
-    auto words = [&]() -> Words {
-      Words w;
-      w.w0 = __ballot_sync(FULL, mybits & 1u);
-      w.w1 = __ballot_sync(FULL, mybits & 2u);
-      w.w2 = __ballot_sync(FULL, mybits & 4u);
-      w.w3 = __ballot_sync(FULL, mybits & 8u);
-      return w;
-    };
     // ---- theta -> (A, B) = (e^theta, e^-theta) / (2 cosh theta)
     {
       const T *th = reinterpret_cast<const T *>(p.theta) + (size_t)chain * M;
       if constexpr (F64) {
 #pragma unroll
         for (int q = 0; q < NV; ++q) {
-          const int j = LM::unit(q, lane);
-          const double2 ab = pair_from_theta(j < M ? th[j] : 0.0);  // padding units: theta = 0
+          const int ju = LM::unit(q, lane), j = wk * MW + ju;
+          const double2 ab = pair_from_theta(ju < MW && j < M ? th[j] : 0.0);  // padding units: theta = 0
           A[q] = ab.x;
           Bv[q] = ab.y;
         }
@@ -467,10 +494,10 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
         float av[2 * NV], bv[2 * NV];
 #pragma unroll
         for (int e = 0; e < 2 * NV; ++e) {
-          const int j = e < NE ? LM::unit(e, lane) : M;
+          const int ju = e < NE ? LM::unit(e, lane) : MW, j = wk * MW + ju;
           av[e] = 0.5f;
           bv[e] = 0.5f;  // padding units: theta = 0
-          if (j < M) {
+          if (ju < MW && j < M) {
             const float x = th[j];
             const float ex = expf(-2.0f * fabsf(x));
             const float big = 1.0f / (1.0f + ex), small = ex * big;
@@ -488,11 +515,10 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
     // ---- exchange: hoppable-cluster bit words of this chain (rules/exchange.py:208-218)
     if (RULE == NK_RULE_EXCHANGE) {
       __syncwarp();
-      const Words sw = words();
       for (int q = 0; q < PROD_HOP_WORDS; ++q) {
         const int c = 32 * q + lane;
-        bool h = false;
-        if (c < C) h = sw.bit(cl[2 * c]) != sw.bit(cl[2 * c + 1]);
+        const int ci = c < C ? cl[2 * c] : 0, cj = c < C ? cl[2 * c + 1] : 0;
+        const bool h = (sbit(ci) != sbit(cj)) && c < C;
         const uint32_t b = __ballot_sync(FULL, h);
         if (lane == 0) hopw[q] = b;
         n_hop += __popc(b);
@@ -536,9 +562,10 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
           acc += LN2 * (log2f(A[q].y + Bv[q].y) - 0.5f * (log2f(A[q].y) + log2f(Bv[q].y)) - 1.0f);
         }
       }
+      acc = gcomb(warp_sum(acc), op_add);  // hidden units: over the lanes and over the warps of the chain
+      T vis = T(0);                         // visible bias: every warp holds all of sigma
       if (s.rbm.a != nullptr) {
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
+        for (int b = 0; b < nbw; ++b) {
           const int idx = 32 * b + lane;
           if (idx < N) {
             T ai;
@@ -546,11 +573,11 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
               ai = 0.5 * rctab[idx].yn;
             else
               ai = 0.5f * LN2 * rctab[idx].y2;
-            acc += ownbit(b) ? -ai : ai;
+            vis += ownbit(b) ? -ai : ai;
           }
         }
       }
-      return warp_sum(acc);
+      return acc + warp_sum(vis);
     };
 
     // ------------------------------------------------------------------ fused local energy of the current sample
@@ -558,7 +585,7 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
     //   0 one site flips, 1 two sites flip to opposite signs (exchange-like), 2 two sites flip to the same sign
     auto eval_cand = [&](auto kind_c, uint32_t d) -> T {
       constexpr int KIND = decltype(kind_c)::value;
-      const int s0 = d & 255, s1 = (d >> 8) & 255;
+      const int s0 = d & CD_SITE_MASK, s1 = (d >> CD_S1_SHIFT) & CD_SITE_MASK;
       const bool p0 = d & CD_POS0;
       V g[NV];
       if constexpr (KIND == 0) {
@@ -588,7 +615,7 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
     };
     // constant of a candidate: fp32 log2 units (added before ex2), fp64 a multiplier
     auto cand_const = [&](uint32_t d) -> T {
-      const int s0 = d & 255, s1 = (d >> 8) & 255;
+      const int s0 = d & CD_SITE_MASK, s1 = (d >> CD_S1_SHIFT) & CD_SITE_MASK;
       if constexpr (F64) {
         double m = 1.0;
         if (d & CD_CHG0) m *= (d & CD_POS0) ? rctab[s0].ep : rctab[s0].em;
@@ -634,7 +661,7 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
               v[jj] = lg2_fast(P);
           }
         }
-        const T tot = bfly<T, NB>(v, lane);
+        const T tot = gcomb(bfly<T, NB>(v, lane), [&](T x, T y) { return bf_op(x, y); });
         if ((lane & 1) == 0 && lane < 2 * NB && (mydesc & CD_VALID)) {
           if constexpr (F64)
             off_l += mymel * (tot * cand_const(mydesc) / nrm);
@@ -647,18 +674,22 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
       if (F64) renormalise();  // keeps every product of M factors inside the double range (see prep: row-sum bound)
       T nrm;                   // fp64: prod_j (A_j + B_j); fp32: its log2
       if constexpr (F64)
-        nrm = warp_prod(lane_norm());
+        nrm = gcomb(warp_prod(lane_norm()), op_mul);
       else
-        nrm = warp_sum(lg2_fast(lane_norm()));
+        nrm = gcomb(warp_sum(lg2_fast(lane_norm())), op_add);
       T off_l = T(0);
       double dl = 0.0;  // diagonal, per-lane partial
-      const Words sw = words();
       // candidates are produced 32 at a time (one per lane); rounds enumerate sites (Ising) or (term, entry) slots
       int rounds0, rounds1 = 0;
       if (s.eloc_kind == 1) {
         // E_loc = J sum_<ij> s_i s_j - h sum_i psi(sigma^(i)) / psi(sigma)        (_ising/jax.py:125-165)
         int zz = 0;
-        for (int e = lane; e < E; e += 32) zz += 1 - 2 * (int)(sw.bit(edges[2 * e]) ^ sw.bit(edges[2 * e + 1]));
+        for (int e0 = 0; e0 < E; e0 += 32) {
+          const int e = e0 + lane;
+          const int ea = e < E ? edges[2 * e] : 0, eb = e < E ? edges[2 * e + 1] : 0;
+          const int par = (int)(sbit(ea) ^ sbit(eb));
+          if (e < E) zz += 1 - 2 * par;
+        }
         dl = s.ising.J * (double)zz;
         rounds0 = s.ising.h != 0.0 ? (N + 31) / 32 : 0;
       } else {
@@ -674,22 +705,25 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
         T mel = T(0);
         if (s.eloc_kind == 1) {
           const int site = 32 * r + lane;
-          if (site < N) d = CD_VALID | CD_CHG0 | (uint32_t)site | ((uint32_t)site << 8) | (sw.bit(site) ? CD_POS0 : 0u);
+          const uint32_t sb = sbit(site < N ? site : 0);
+          if (site < N) d = CD_VALID | CD_CHG0 | (uint32_t)site | ((uint32_t)site << CD_S1_SHIFT) | (sb ? CD_POS0 : 0u);
           mel = (T)(-s.ising.h);
         } else {
           const int gi = r < rounds0 ? 0 : 1;
           const nk_localop_group_t &G = s.localop.groups[gi];
           const int rows = 1 << G.n_sites, ncm = G.ncmax;
-          const uint8_t *sites = aux + L.lop_sites_off[gi];
+          const uint16_t *sites = reinterpret_cast<const uint16_t *>(aux + L.lop_sites_off[gi]);
           const T *dg = reinterpret_cast<const T *>(aux + L.lop_diag_off[gi]);
           const T *ml = reinterpret_cast<const T *>(aux + L.lop_mel_off[gi]);
           const uint8_t *cd = aux + L.lop_code_off[gi];
           const int slots = G.n_ops * max(ncm, 1);
           const int q = 32 * (gi == 0 ? r : r - rounds0) + lane;
-          if (q < slots) {
-            const int o = ncm > 1 ? q / ncm : q, c = ncm > 1 ? q - o * ncm : 0;
-            const int s0 = sites[2 * o], s1 = sites[2 * o + 1];
-            const int x0 = (int)sw.bit(s0), x1 = G.n_sites == 2 ? (int)sw.bit(s1) : 0;
+          const bool live = q < slots;
+          const int o = live ? (ncm > 1 ? q / ncm : q) : 0, c = live && ncm > 1 ? q - o * ncm : 0;
+          const int s0 = sites[2 * o], s1 = sites[2 * o + 1];
+          const int x0 = (int)sbit(s0), x1b = (int)sbit(s1);  // all lanes shuffle
+          if (live) {
+            const int x1 = G.n_sites == 2 ? x1b : 0;
             const int row = G.n_sites == 2 ? 2 * x0 + x1 : x0;  // _state_to_number: first site most significant
             if (c == 0) dl += (double)dg[o * rows + row];
             if (ncm > 0) {
@@ -701,7 +735,7 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
                 if (!ch0 && !ch1) {
                   off_l += mel;  // an entry that maps sigma onto itself: ratio 1
                 } else {
-                  d = CD_VALID | (uint32_t)s0 | ((uint32_t)s1 << 8) | (ch0 ? CD_CHG0 : 0u) | (ch1 ? CD_CHG1 : 0u) |
+                  d = CD_VALID | (uint32_t)s0 | ((uint32_t)s1 << CD_S1_SHIFT) | (ch0 ? CD_CHG0 : 0u) | (ch1 ? CD_CHG1 : 0u) |
                       (xp0 == 0 ? CD_POS0 : 0u) | (xp1 == 0 ? CD_POS1 : 0u);
                 }
               }
@@ -727,20 +761,19 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
       ++sweep_idx;
       if (sw < 0) return;
       const size_t o = (size_t)chain * s.chain_length + sw;
-      if (s.samples_out != nullptr) {
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
+      if (s.samples_out != nullptr && wk == 0) {
+        for (int b = 0; b < nbw; ++b) {
           const int idx = 32 * b + lane;
           if (idx < N) s.samples_out[o * N + idx] = ownbit(b) ? (int8_t)-1 : (int8_t)1;
         }
       }
       if (s.logp_out != nullptr) {
         const T lp = logpsi_now();
-        if (lane == 0) reinterpret_cast<T *>(s.logp_out)[o] = pw * lp;
+        if (lane == 0 && wk == 0) reinterpret_cast<T *>(s.logp_out)[o] = pw * lp;
       }
       if (s.eloc_kind != 0) {
         const T e = local_energy();
-        if (lane == 0) store_as<T>(s.eloc_out, o, e, s.eloc_dtype);
+        if (lane == 0 && wk == 0) store_as<T>(s.eloc_out, o, e, s.eloc_dtype);
       }
     };
 
@@ -788,7 +821,7 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
             const int fx = rc.fx, fy = rc.fy;
             const bool pos = sbit(site) != 0;  // sigma = -1 -> +1
             const T P = pos ? lane_product<V, NV>(Bv, A, g) : lane_product<V, NV>(A, Bv, g);
-            const int Rp = __reduce_add_sync(FULL, fxlog(P));
+            const int Rp = gcomb(__reduce_add_sync(FULL, fxlog(P)), op_add);
             const int X = (int)((uint32_t)Rp - (uint32_t)R + (uint32_t)(pos ? fx + fy : fx - fy));
             bool acc;
             if constexpr (F64) {
@@ -797,7 +830,8 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
               else if (thr >= X + PROD_FX_BAND)
                 acc = false;
               else
-                acc = exact_accept(P, lane_norm(), pos ? rc.xn + rc.yn : rc.xn - rc.yn, __shfl_sync(FULL, u_l, k), pw, 0.0);
+                acc = exact_decide(gcomb(exact_logratio(P, lane_norm()), op_add), pos ? rc.xn + rc.yn : rc.xn - rc.yn,
+                                   __shfl_sync(FULL, u_l, k), pw, 0.0);
             } else {
               acc = thr < X;
             }
@@ -879,7 +913,7 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
                 else if (thr >= X + PROD_FX_BAND)
                   acc = false;
                 else
-                  acc = exact_accept(P, lane_norm(), rp.xn + rp.yn + rm.xn - rm.yn, __shfl_sync(FULL, u_l, k), pw,
+                  acc = exact_decide(exact_logratio(P, lane_norm()), rp.xn + rp.yn + rm.xn - rm.yn, __shfl_sync(FULL, u_l, k), pw,
                                      log((double)n_hop) - log((double)nhp));
               } else {
                 acc = thr < X;
@@ -908,13 +942,14 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
     }
     if (s.eloc_only) continue;
     // ---- write the chain state back
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int idx = 32 * b + lane;
-      if (idx < N) s.sigma[(size_t)chain * N + idx] = ownbit(b) ? (int8_t)-1 : (int8_t)1;
+    if (wk == 0) {
+      for (int b = 0; b < nbw; ++b) {
+        const int idx = 32 * b + lane;
+        if (idx < N) s.sigma[(size_t)chain * N + idx] = ownbit(b) ? (int8_t)-1 : (int8_t)1;
+      }
     }
     const T lp = logpsi_now();
-    if (lane == 0) {
+    if (lane == 0 && wk == 0) {
       reinterpret_cast<T *>(s.log_prob)[chain] = pw * lp;
       s.n_accepted[chain] += (int64_t)nacc;
     }
@@ -922,15 +957,15 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
   }
 }
 
-// host-side launcher of one instantiation (defined in sweep_prod_inst_*.cu)
-template <typename T, int NFULL, int TAIL, int RULE>
+// host-side launcher of one instantiation (called from sweep_prod_inst_*.cu)
+template <typename T, int NFULL, int TAIL, int RULE, bool MULTI>
 int launch_prod(cudaStream_t stream, const ProdArgs &a) {
-  auto kern = sweep_prod_kernel<T, NFULL, TAIL, RULE>;
-  constexpr int WARPS = prod::ProdWarps<T, RULE>::value;
+  auto kern = sweep_prod_kernel<T, NFULL, TAIL, RULE, MULTI>;
   NK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.L.smem_bytes));
-  const int64_t need = (a.s.B + WARPS - 1) / WARPS;
+  const int groups = a.L.warps / a.L.kw;  // chains in flight per CTA
+  const int64_t need = (a.s.B + groups - 1) / groups;
   const int64_t cap = num_sms();
-  kern<<<(int)(need < cap ? need : cap), WARPS * 32, a.L.smem_bytes, stream>>>(a);
+  kern<<<(int)(need < cap ? need : cap), a.L.warps * 32, a.L.smem_bytes, stream>>>(a);
   NK_LAUNCH_OK();
   return NK_OK;
 }
@@ -939,5 +974,8 @@ int launch_prod_f32_local(cudaStream_t stream, const ProdArgs &a, int nfull, int
 int launch_prod_f32_exchange(cudaStream_t stream, const ProdArgs &a, int nfull, int tail);
 int launch_prod_f64_local(cudaStream_t stream, const ProdArgs &a, int nfull, int tail);
 int launch_prod_f64_exchange(cudaStream_t stream, const ProdArgs &a, int nfull, int tail);
+// several warps per chain (M > 512): LocalRule only
+int launch_prod_f32_local_multi(cudaStream_t stream, const ProdArgs &a, int nfull, int tail);
+int launch_prod_f64_local_multi(cudaStream_t stream, const ProdArgs &a, int nfull, int tail);
 
 }  // namespace nk

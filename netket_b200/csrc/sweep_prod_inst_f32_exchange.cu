@@ -1,11 +1,11 @@
-// Instantiations of sweep_prod_kernel<float, NFULL, TAIL, NK_RULE_EXCHANGE> (one translation unit per (dtype, rule): parallel build).
+// Instantiations of sweep_prod_kernel<float, NFULL, TAIL, NK_RULE_EXCHANGE, MULTI=false> (one translation unit per variant: parallel build).
 #include "sweep_prod.cuh"
 
 namespace nk {
 
 int launch_prod_f32_exchange(cudaStream_t stream, const ProdArgs &a, int nfull, int tail) {
 #define NK_PROD_CASE(NF, TL) \
-  if (nfull == NF && tail == TL) return launch_prod<float, NF, TL, NK_RULE_EXCHANGE>(stream, a);
+  if (nfull == NF && tail == TL) return launch_prod<float, NF, TL, NK_RULE_EXCHANGE, false>(stream, a);
   NK_PROD_CASE(0, 1)
   NK_PROD_CASE(0, 2)
   NK_PROD_CASE(1, 0)

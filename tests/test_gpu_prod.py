@@ -314,6 +314,65 @@ def test_prod_standalone_eloc_hands_over_for_large_weights(cuda):
     sig = torch.from_numpy(ohilbert.random_state(2, 50, 16)).cuda()
     assert np.array_equal(vs._eloc_on_samples(op, sig, path=0).cpu().numpy(), vs._eloc_on_samples(op, sig, path=1).cpu().numpy())
     with pytest.raises(nk.NkError):
-        nk.vqs.MCState(nk.sampler.MetropolisLocal(nk.hilbert.Spin(0.5, 130), n_chains=16), nk.models.RBM(alpha=1),
-                       n_samples=16, seed=1)._eloc_on_samples(nk.operator.Ising(nk.hilbert.Spin(0.5, 130), nk.graph.Hypercube(130, 1), h=1.0),
-                                                              torch.ones((4, 130), dtype=torch.int8, device="cuda"), path=PROD)
+        # beyond the product-form kernels' limits (N <= 1024): NK_PATH_PROD must refuse, not fall back
+        nk.vqs.MCState(nk.sampler.MetropolisLocal(nk.hilbert.Spin(0.5, 1030), n_chains=16), nk.models.RBM(alpha=1),
+                       n_samples=16, seed=1)._eloc_on_samples(nk.operator.Ising(nk.hilbert.Spin(0.5, 1030), nk.graph.Hypercube(1030, 1), h=1.0),
+                                                              torch.ones((4, 1030), dtype=torch.int8, device="cuda"), path=PROD)
+
+
+# ----------------------------------------------------------------------------------------- large systems
+# M > 512: several warps per chain (partial sums combined through shared memory);  N > 128: sigma bits beyond four words;
+# tables larger than shared memory: rows read through L2 (generic-address loads).
+LARGE = [("local", 20, 1, 32, 0.01, None, 1),      # N=20, M=640: 2 warps per chain
+         ("local", 16, 1, 100, 0.005, None, 1),    # N=16, M=1600: 4-5 warps per chain
+         ("local", 12, 2, 4, 0.02, None, 1),       # N=144, M=576: 2 warps per chain, N > 128
+         ("local", 14, 2, 2, 0.03, None, 1),       # N=196, M=392: one warp per chain, table (326 KB fp32) not resident
+         ("exchange", 12, 2, 1, 0.05, 0, 1)]       # N=144 exchange, 288 clusters
+
+
+@pytest.mark.parametrize("rule,L,n_dim,alpha,std,total_sz,d_max", LARGE)
+def test_prod_large_reproduces_oracle_chain_fp64(cuda, rule, L, n_dim, alpha, std, total_sz, d_max):
+    nk = _nk()
+    B, CL = 12, 2
+    g, hi, (W, b, a), var, model, sa, clusters, e, col = _case(nk, rule, L, n_dim, alpha, np.float64, std, B, total_sz, d_max)
+    st = sa.init_state(model, var, seed=15324)
+    seed, t0 = st.rng
+    ref = osampler.sample_chain(rule, st.σ.cpu().numpy(), W, b, a, chain_length=CL, seed=seed, t0=t0, clusters=clusters)
+    (samples, logp), st2 = sa.sample(model, var, state=st, chain_length=CL, return_log_probabilities=True, _path=PROD)
+    assert np.array_equal(samples.cpu().numpy(), ref["samples"])
+    scale = max(1.0, np.abs(ref["log_prob_samples"]).max())
+    np.testing.assert_allclose(logp.cpu().numpy(), ref["log_prob_samples"], rtol=1e-10, atol=1e-11 * scale)
+    np.testing.assert_allclose(st2.log_prob.cpu().numpy(), ref["log_prob"], rtol=1e-10, atol=1e-11 * scale)
+    assert np.array_equal(st2.n_accepted_proc.cpu().numpy(), ref["n_accepted"])
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("rule,L,n_dim,alpha,std,total_sz,d_max", LARGE)
+def test_prod_large_fused_eloc(cuda, dtype, rule, L, n_dim, alpha, std, total_sz, d_max):
+    nk = _nk()
+    B = 30
+    g, hi, (W, b, a), var, model, sa, clusters, e, col = _case(nk, rule, L, n_dim, alpha, dtype, std, B, total_sz, d_max)
+    if rule == "local":
+        op = nk.operator.Ising(hi, g, h=2.0)
+        conn = lambda x: oops.ising_conn_padded(x, e, 2.0, 1.0)  # noqa: E731
+    else:
+        op = nk.operator.Heisenberg(hi, g)
+        tables = oops.heisenberg_tables(e, col, 1.0, ograph.is_bipartite(g.n_nodes, e))
+        conn = lambda x: oops.local_operator_conn_padded(x, tables)  # noqa: E731
+    st = sa.init_state(model, var, seed=11)
+    samples, _, eloc, st2 = sa._launch(model, var, st, 2, n_discard=1, operator=op, path=PROD)
+    ref = oest.local_estimators(samples.cpu().numpy(), conn, *_f64(W, b, a))
+    tol = 1e-11 if dtype == np.float64 else 2e-5
+    np.testing.assert_allclose(eloc.cpu().numpy(), ref, rtol=tol, atol=tol * np.abs(ref).max())
+    # fp32: the chain itself follows the oracle's up to accept-boundary ties
+    if dtype == np.float32:
+        seed, t0 = st.rng
+        words, u32 = orng.proposal_stream(seed, t0, 3 * sa.sweep_size, np.arange(B), np.float32)
+        r = osampler.sample_chain(rule, st.σ.cpu().numpy(), *_f64(W, b, a), chain_length=3, stream=(words[..., 0], u32.astype(np.float64)),
+                                  clusters=clusters)
+        same = np.all(samples.cpu().numpy() == r["samples"][:, 1:], axis=(1, 2))
+        assert same.mean() >= 0.8, same.mean()
+    # stand-alone estimator on the same samples
+    vs = nk.vqs.MCState(sa, model, variables=var, n_samples=B, seed=1)
+    alone = vs._eloc_on_samples(op, samples, path=PROD)
+    np.testing.assert_allclose(alone.cpu().numpy(), ref, rtol=tol, atol=tol * np.abs(ref).max())

@@ -1,9 +1,9 @@
 """Developer probe: throughput of the fused sweep + E_loc kernels on the BASELINE.json configurations other than cfg-3.
 
-    python tools/prod_probe.py --cfg 2|4|1 [--chains N] [--cl K] [--dtype float64] [--path 0|1|3] [--reps 3]
+    python tools/prod_probe.py --cfg 1|2|4|5 [--chains N] [--cl K] [--dtype float64] [--path 0|1|3] [--reps 3]
 
 cfg 1: Ising1d L=20, RBM alpha=1, MetropolisLocal;  cfg 2: Heisenberg1d L=22 total_sz=0, RBM alpha=2, MetropolisExchange;
-cfg 4: J1-J2 10x10 (J2=0.5), RBM alpha=4, MetropolisExchange (d_max given by --dmax).
+cfg 4: J1-J2 10x10 (J2=0.5), RBM alpha=4, MetropolisExchange (d_max given by --dmax);  cfg 5: TFIM 20x20, RBM alpha=8 (N=400, M=3200).
 Prints samples/s (CUDA events on the launching stream) and the acceptance.  Not part of the product or of bench.py.
 """
 
@@ -37,6 +37,12 @@ def main():
         hi = nk.hilbert.Spin(0.5, g.n_nodes)
         op = nk.operator.Ising(hi, g, h=1.0)
         alpha = 1
+        sa = nk.sampler.MetropolisLocal(hi, n_chains=a.chains)
+    elif a.cfg == 5:
+        g = nk.graph.Hypercube(20, 2)
+        hi = nk.hilbert.Spin(0.5, g.n_nodes)
+        op = nk.operator.Ising(hi, g, h=3.0)
+        alpha = 8
         sa = nk.sampler.MetropolisLocal(hi, n_chains=a.chains)
     elif a.cfg == 2:
         g = nk.graph.Hypercube(22, 1)
