@@ -181,6 +181,19 @@ int nk_stats_partial(void *stream, const void *data, int32_t dtype, int64_t n_ch
 /* host-only arithmetic: sums_host = all-reduced phase-1 partials; out_host = {mean, error_of_mean, variance, tau_corr, R_hat} */
 int nk_stats_finalize(const double *sums_host, double mean, int64_t n_chains_total, int64_t L, double *out_host);
 
+/* Forces F_k = < d log psi / d p_k * (E_loc - mean) > of the RBM over a batch of samples: the vjp of
+ * netket/vqs/mc/mc_state/expect_forces.py:69-112 (`forces_expect_hermitian`) in closed form
+ * (d/dW_ij = sigma_i tanh theta_j, d/db_j = tanh theta_j, d/da_i = sigma_i).
+ *   nk_forces_rbm       sums[N*M | M | N] (doubles, device; zeroed by the call) = sum_s dlogpsi(sigma_s) * (eloc_s - mean)
+ *                       over this device's Ns samples; only these sums cross GPUs (all-reduce by the caller);
+ *   nk_forces_finalize  out[k] = (dtype) (sums[k] * scale), scale = 1 / n_samples_total (x 2 for the gradient of a
+ *                       real-parameter ansatz, netket/vqs/mc/common.py:103-118 `force_to_grad`).
+ * workspace: nk_forces_workspace_bytes(rbm, Ns) (theta of the batch + theta-GEMM scratch). */
+int64_t nk_forces_workspace_bytes(const nk_rbm_t *rbm, int64_t Ns);
+int nk_forces_rbm(void *stream, const nk_rbm_t *rbm, const int8_t *samples, int64_t Ns, const void *eloc, int32_t eloc_dtype,
+                  double mean, double *sums, void *workspace);
+int nk_forces_finalize(void *stream, const double *sums, double scale, int64_t n, void *out, int32_t dtype);
+
 /* ---------------------------------------------------------------------------------------------
  * Host-buffer API: one VMC inner-loop step with HOST pointers (what bench.py's `e2e` times).
  * The context owns the device buffers (parameters, chains, operator tables, E_loc).

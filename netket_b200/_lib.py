@@ -77,6 +77,10 @@ SYMBOLS = {
                                     C.c_int32, C.c_int32, C.c_void_p]),
     "nk_eloc_localop_rbm": (C.c_int, [C.c_void_p, C.POINTER(nk_rbm_t), C.POINTER(nk_localop_t), C.c_void_p, C.c_int64,
                                       C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "nk_forces_workspace_bytes": (C.c_int64, [C.POINTER(nk_rbm_t), C.c_int64]),
+    "nk_forces_rbm": (C.c_int, [C.c_void_p, C.POINTER(nk_rbm_t), C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_double,
+                                C.c_void_p, C.c_void_p]),
+    "nk_forces_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_int64, C.c_void_p, C.c_int32]),
     "nk_stats_partial": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_double, C.c_void_p]),
     "nk_stats_finalize": (C.c_int, [C.POINTER(C.c_double), C.c_double, C.c_int64, C.c_int64, C.POINTER(C.c_double)]),
     "nk_ctx_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32,

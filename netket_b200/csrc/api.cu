@@ -52,6 +52,10 @@ int random_state(cudaStream_t stream, int8_t *sigma, int64_t B, int32_t N, int32
 int64_t theta_gemm_workspace_bytes(const nk_rbm_t &rbm, int64_t B);
 int theta_gemm(cudaStream_t stream, const nk_rbm_t &rbm, const int8_t *sigma, int64_t B, void *theta_out, void *workspace);
 
+int forces_sums(cudaStream_t stream, const nk_rbm_t &rbm, const int8_t *sigma, const void *theta, const void *eloc, int32_t eloc_dtype,
+                int64_t Ns, double mean, double *sums);
+int forces_finalize(cudaStream_t stream, const double *sums, double scale, int64_t n, void *out, int32_t dtype);
+
 static int check_rbm(const nk_rbm_t *rbm, const char *who) {
   NK_CHECK_ARG(rbm != nullptr, "%s: rbm is NULL", who);
   NK_CHECK_ARG(rbm->W != nullptr, "%s: rbm.W is NULL", who);
@@ -304,6 +308,35 @@ int nk_eloc_localop_rbm(void *stream, const nk_rbm_t *rbm, const nk_localop_t *o
   NK_CHECK_ARG(B >= 0 && (B == 0 || (sigma && eloc_out)), "nk_eloc_localop_rbm: bad batch / NULL buffer");
   NK_CHECK_ARG(eloc_dtype == NK_F32 || eloc_dtype == NK_F64, "nk_eloc_localop_rbm: bad eloc_dtype");
   return eloc_dispatch((cudaStream_t)stream, rbm, nullptr, op, sigma, B, eloc_out, eloc_dtype, path, workspace, "nk_eloc_localop_rbm");
+}
+
+int64_t nk_forces_workspace_bytes(const nk_rbm_t *rbm, int64_t Ns) {
+  if (check_rbm(rbm, "nk_forces_workspace_bytes") || Ns < 0) return -1;
+  return (int64_t)(ws_theta_bytes(rbm, Ns) + (size_t)theta_gemm_workspace_bytes(*rbm, Ns));
+}
+
+int nk_forces_rbm(void *stream, const nk_rbm_t *rbm, const int8_t *samples, int64_t Ns, const void *eloc, int32_t eloc_dtype,
+                  double mean, double *sums, void *workspace) {
+  int rc = check_rbm(rbm, "nk_forces_rbm");
+  if (rc) return rc;
+  NK_CHECK_ARG(Ns >= 0 && sums != nullptr, "nk_forces_rbm: bad arguments");
+  NK_CHECK_ARG(Ns == 0 || (samples && eloc && workspace), "nk_forces_rbm: NULL buffer");
+  NK_CHECK_ARG(eloc_dtype == NK_F32 || eloc_dtype == NK_F64, "nk_forces_rbm: bad eloc_dtype");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)rbm->N * rbm->M + rbm->M + rbm->N;
+  NK_CUDA_OK(cudaMemsetAsync(sums, 0, n * sizeof(double), st));
+  if (Ns == 0) return NK_OK;
+  void *theta = workspace;
+  void *scratch = reinterpret_cast<char *>(workspace) + ws_theta_bytes(rbm, Ns);
+  rc = theta_gemm(st, *rbm, samples, Ns, theta, scratch);
+  if (rc) return rc;
+  return forces_sums(st, *rbm, samples, theta, eloc, eloc_dtype, Ns, mean, sums);
+}
+
+int nk_forces_finalize(void *stream, const double *sums, double scale, int64_t n, void *out, int32_t dtype) {
+  NK_CHECK_ARG(n >= 0 && (n == 0 || (sums && out)), "nk_forces_finalize: bad arguments");
+  NK_CHECK_ARG(dtype == NK_F32 || dtype == NK_F64, "nk_forces_finalize: bad dtype");
+  return forces_finalize((cudaStream_t)stream, sums, scale, n, out, dtype);
 }
 
 int nk_stats_partial(void *stream, const void *data, int32_t dtype, int64_t n_chains, int64_t L, int32_t phase, double shift,

@@ -421,20 +421,24 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
   // generic addresses so that one instruction stream serves both kinds of row.
   uint32_t lane_row = s32(smem) + 16u * lane;
   uint32_t lane_tail = s32(smem) + (uint32_t)LM::TAIL_OFF + (uint32_t)LM::TAIL_LANE * lane;
-  const unsigned char *sbase = smem + (size_t)wk * ROW_BYTES;    // generic address of the resident rows (this warp's segment)
-  const unsigned char *gbase = p.gtab + (size_t)wk * ROW_BYTES;
-  const int row_stride = L.row_bytes;
+  // generic addresses of this lane's first element in row 0 (this warp's segment): resident copy / global table.
+  // Kept opaque so that they stay in registers (no cvta / constant-bank reloads per row); offsets are 32-bit.
+  const unsigned char *sbase = smem + (size_t)wk * ROW_BYTES + 16 * lane;
+  const unsigned char *gbase = p.gtab + (size_t)wk * ROW_BYTES + 16 * lane;
+  int tail_delta = LM::TAIL_OFF + LM::TAIL_LANE * lane - 16 * lane;  // tail element relative to the above (may be negative)
+  uint32_t row_stride = (uint32_t)L.row_bytes;
   int n_res = L.n_res;
   int sweep_size = s.sweep_size;
-  asm volatile("" : "+r"(lane_row), "+r"(lane_tail), "+r"(n_res), "+r"(sweep_size));
+  asm volatile("" : "+r"(lane_row), "+r"(lane_tail), "+r"(n_res), "+r"(sweep_size), "+r"(tail_delta), "+r"(row_stride));
+  asm volatile("" : "+l"(sbase), "+l"(gbase));
 
   auto fetch = [&](int site, V(&g)[NV]) {
     if constexpr (!GENERIC_ROWS) {
       const uint32_t o = (uint32_t)site * (uint32_t)ROW_BYTES;
       load_row_s<NFULL, TAIL>(lane_row + o, lane_tail + o, g);
     } else {
-      const unsigned char *row = (site < n_res ? sbase : gbase) + (size_t)site * row_stride;
-      load_row_p<NFULL, TAIL>(row + 16 * lane, row + LM::TAIL_OFF + LM::TAIL_LANE * lane, g);
+      const unsigned char *row = (site < n_res ? sbase : gbase) + (uint32_t)site * row_stride;
+      load_row_p<NFULL, TAIL>(row, row + (ptrdiff_t)tail_delta, g);
     }
   };
 

@@ -73,6 +73,7 @@ class MCState:
         self._samples = None
         self._eloc_cache = {}
         self._eloc_ws = None
+        self._forces_ws = None
         self._chain_length = None
         _, ws = world()
         if n_samples is not None and n_samples_per_rank is not None:
@@ -269,8 +270,54 @@ class MCState:
         """<O> with MC statistics (state.py:695-712)."""
         return statistics(self.local_estimators(op))
 
-    def expect_and_grad(self, op, **kw):
-        raise NotImplementedError("expect_and_grad is the next tier (SURVEY.md §8f rank 1) and is not built yet")
+    def expect_and_forces(self, op, *, mutable=False):
+        """``(Stats, forces)`` with ``forces[k] = < d log psi / d p_k * (E_loc - <E_loc>) >`` in the layout of
+        ``self.parameters`` (netket/vqs/mc/mc_state/expect_forces.py:39-112).  The RBM's log-derivatives are closed
+        forms, so the vjp is one contraction over the samples (nk_forces_rbm); between GPUs only the
+        ``N*M + M + N`` double sums are all-reduced."""
+        return self._forces(op, 1.0)
+
+    def expect_and_grad(self, op, *, use_covariance=None, mutable=False):
+        """``(Stats, grad)``: for the real-parameter RBM the gradient of <O> is ``2 Re F``
+        (``force_to_grad``, netket/vqs/mc/common.py:103-118; hermitian operators only, as the reference's default)."""
+        if use_covariance is False:
+            raise NotImplementedError("expect_and_grad(use_covariance=False): the non-hermitian estimator is not implemented")
+        return self._forces(op, 2.0)
+
+    def _forces(self, op, factor):
+        from .stats import _allreduce
+
+        eloc = self.local_estimators(op)
+        stats = statistics(eloc)
+        samples = self.samples
+        rbm = RBM.c_struct(self._variables)
+        W, b, a = RBM.unpack(self._variables)
+        dev = W.device
+        N, M = rbm.N, rbm.M
+        s8 = samples.reshape(-1, N).contiguous()
+        e = eloc.reshape(-1).contiguous()
+        Ns = s8.shape[0]
+        L = _lib.lib()
+        nbytes = int(L.nk_forces_workspace_bytes(C.byref(rbm), Ns))
+        if self._forces_ws is None or self._forces_ws.numel() < nbytes or self._forces_ws.device != dev:
+            self._forces_ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        n = N * M + M + N
+        sums = torch.empty(n, dtype=torch.float64, device=dev)
+        _, ws = world()
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            _lib.check(L.nk_forces_rbm(st, C.byref(rbm), _lib.ptr(s8), Ns, _lib.ptr(e), _lib.dtype_code(e.dtype), float(stats.mean),
+                                       _lib.ptr(sums), _lib.ptr(self._forces_ws)))
+            _allreduce(sums)  # the only cross-device traffic of the gradient: n_parameters doubles
+            out = torch.empty(n, dtype=W.dtype, device=dev)
+            _lib.check(L.nk_forces_finalize(st, _lib.ptr(sums), factor / float(Ns * ws), n, _lib.ptr(out), _lib.dtype_code(W.dtype)))
+        dense = {"kernel": out[: N * M].reshape(N, M)}
+        if b is not None:
+            dense["bias"] = out[N * M: N * M + M]
+        forces = {"Dense": dense}
+        if a is not None:
+            forces["visible_bias"] = out[N * M + M:]
+        return stats, forces
 
     def __repr__(self):
         return (f"MCState(\n  hilbert = {self.hilbert},\n  sampler = {self._sampler},\n  n_samples = {self.n_samples},\n"

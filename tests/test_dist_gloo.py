@@ -84,6 +84,19 @@ def _worker(rank, ws, port, out):
     run_full = osampler.sample_chain("local", sig_full, W, b, a, chain_length=2, seed=5)
     run_mine = osampler.sample_chain("local", sig_mine, W, b, a, chain_length=2, seed=5, chain_offset=12 * rank)
     res["chains_ok"] = bool(np.array_equal(run_mine["samples"], run_full["samples"][12 * rank:12 * rank + 12]))
+    # --- forces: every rank contributes the sums over its shard of samples (what nk_forces_rbm produces); the all-reduced
+    # sums scaled by 1 / n_samples_total equal the forces of the full batch (expect_forces.py:81-104)
+    from oracle import forces as oforces
+
+    samples = run_full["samples"]
+    eloc = np.random.default_rng(4).normal(size=samples.shape[:2])
+    mine = slice(12 * rank, 12 * rank + 12)
+    f_mine = oforces.forces(samples[mine], eloc[mine], W, b, a, mean=eloc.mean(), n_total=1)  # raw sums of this shard
+    sums = torch.from_numpy(np.concatenate([f_mine["W"].ravel(), f_mine["b"], f_mine["a"]]))
+    nkstats._allreduce(sums)
+    f_full = oforces.forces(samples, eloc, W, b, a)
+    ref_vec = np.concatenate([f_full["W"].ravel(), f_full["b"], f_full["a"]])
+    res["forces_ok"] = bool(np.allclose(sums.numpy() / eloc.size, ref_vec, rtol=1e-12, atol=1e-14))
     out[rank] = res
     dist.barrier()
     dist.destroy_process_group()
@@ -101,5 +114,5 @@ def test_two_process_gloo():
         assert r["chains"] == (32, 16)
         assert r["rounded"] == (34, 17, True)
         assert r["default"] == 32  # 16 chains per rank
-        assert r["stats_ok"] and r["init_ok"] and r["chains_ok"]
+        assert r["stats_ok"] and r["init_ok"] and r["chains_ok"] and r["forces_ok"]
     assert r0["seed"] == r1["seed"]

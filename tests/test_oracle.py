@@ -204,3 +204,54 @@ def test_statistics_identities():
     stb = ostats.statistics(big)
     np.testing.assert_allclose(stb["error_of_mean"], np.sqrt(big.mean(axis=1).var() / 64))
     assert 0.9 < stb["R_hat"] < 1.1
+
+
+def test_rbm_log_derivatives_match_finite_differences():
+    """Pins oracle/forces.py: the closed-form dlogpsi/dp equals the numerical derivative of oracle.rbm.logpsi, and the
+    forces follow expect_forces.py:81-104 (centred local energies, division by n_samples)."""
+    from oracle import forces as oforces
+
+    N, alpha = 5, 2
+    W, b, a = rbm.init_params(N, alpha, std=0.4)
+    sig = hilbert.random_state(1, 7, N)
+    OW, Ob, Oa = oforces.log_derivatives(sig, W, b, a)
+    h = 1e-6
+    for (i, j) in [(0, 0), (3, 7), (4, 9)]:
+        Wp, Wm = W.copy(), W.copy()
+        Wp[i, j] += h
+        Wm[i, j] -= h
+        fd = (rbm.logpsi(sig, Wp, b, a) - rbm.logpsi(sig, Wm, b, a)) / (2 * h)
+        np.testing.assert_allclose(OW[:, i, j], fd, rtol=1e-7, atol=1e-8)
+    for j in (0, 5):
+        bp, bm = b.copy(), b.copy()
+        bp[j] += h
+        bm[j] -= h
+        np.testing.assert_allclose(Ob[:, j], (rbm.logpsi(sig, W, bp, a) - rbm.logpsi(sig, W, bm, a)) / (2 * h), rtol=1e-7, atol=1e-8)
+    ap, am = a.copy(), a.copy()
+    ap[2] += h
+    am[2] -= h
+    np.testing.assert_allclose(Oa[:, 2], (rbm.logpsi(sig, W, b, ap) - rbm.logpsi(sig, W, b, am)) / (2 * h), rtol=1e-7, atol=1e-8)
+    e = np.random.default_rng(0).normal(size=7)
+    f = oforces.forces(sig, e, W, b, a)
+    w = (e - e.mean()) / 7
+    np.testing.assert_allclose(f["W"], np.einsum("s,sij->ij", w, OW), rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(f["b"], w @ Ob, rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(f["a"], w @ Oa, rtol=1e-12, atol=1e-14)
+    # exact gradient of <H>: for exact sampling (all states weighted by |psi|^2) 2 F equals d<H>/dp by finite differences
+    e_g, _ = graph.hypercube_edges(N, 1)
+    conn = lambda x: ops.ising_conn_padded(x, e_g, 1.0, 1.0)  # noqa: E731
+    states = hilbert.all_states(N)
+
+    def energy(Wx):
+        psi = rbm.to_array(Wx, b, a, states)
+        return ed.expectation(conn, N, psi)
+
+    p = sampler.exact_distribution(W, b, a, states)
+    eloc = estimators.local_value_kernel(states, conn, W, b, a)
+    OWs, _, _ = oforces.log_derivatives(states, W, b, a)
+    mean = float(p @ eloc)
+    g_exact = 2.0 * np.einsum("s,sij->ij", p * (eloc - mean), OWs)
+    Wp, Wm = W.copy(), W.copy()
+    Wp[1, 3] += h
+    Wm[1, 3] -= h
+    np.testing.assert_allclose(g_exact[1, 3], (energy(Wp) - energy(Wm)) / (2 * h), rtol=1e-6, atol=1e-8)
