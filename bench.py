@@ -114,8 +114,9 @@ def run_cpu(dtype, steps, warmup):
     """The reference algorithm on the host cores, on a bounded sample of the workload (see cpu_baseline.sample)."""
     from oracle import reference_algorithm as ra
 
+    # all the host threads the box has (torchrun exports OMP_NUM_THREADS=1, which would otherwise cap the baseline at one core)
     val, ms, threads = ra.time_vmc_steps(N_SITES, N_HIDDEN, CPU_SAMPLE_CHAINS, 1, edges_np(), H_FIELD, J_COUP, np.dtype(dtype).type,
-                                         steps=steps, warmup=warmup, seed=SAMPLER_SEED)
+                                         steps=steps, warmup=warmup, seed=SAMPLER_SEED, threads=os.cpu_count())
     sample = (f"{CPU_SAMPLE_CHAINS} chains x 1 (sweep + E_loc) per step, {steps} timed steps after {warmup} warm-up; same "
               "N, M, h, J, parameters and algorithmic structure as the GPU workload; throughput is linear in the number "
               "of chains once the GEMMs saturate the cores")
