@@ -299,7 +299,7 @@ static bool prod_layout(const SweepKernelArgs &a, const ProdShape &ps, ProdLayou
       L->warps = groups * ps.kw;
     }
     xs_bytes = multi ? (L->warps / ps.kw) * 2 * ps.kw * 256 : 0;
-    const int budget = 227 * 1024 - (L->aux_bytes + hop_bytes + xs_bytes + 16);
+    const int budget = 227 * 1024 - (L->aux_bytes + hop_bytes + xs_bytes + 16);  // all offsets are 16-byte multiples
     if (budget < 0) return false;
     n_res = budget / L->row_bytes;
     if (n_res > N) n_res = N;

@@ -11,12 +11,14 @@
 //     128 configurations: threads convert sigma (int8) to bf16 straight into the A tile, one thread issues the MMAs
 //     (UMMA 128 x NT x 16, cta_group::1), tcgen05.commit signals an mbarrier, and the four warps read their TMEM lane
 //     quarter with tcgen05.ld, add the bias and store theta.
-// fp64 (and shapes outside the tensor-core kernel's limits): the CUDA-core kernel rbm_logpsi_kernel.
+// fp64: FP64 tensor cores (DMMA), theta_dmma.cu.  Shapes outside both kernels' limits: the CUDA-core kernel rbm_logpsi_kernel.
 #include "kernels.cuh"
 
 namespace nk {
 
 int rbm_logpsi(cudaStream_t stream, const nk_rbm_t &rbm, const int8_t *sigma, int64_t B, void *out, void *theta_out);
+bool theta_dmma_supported(const nk_rbm_t &rbm);
+int theta_dmma(cudaStream_t stream, const nk_rbm_t &rbm, const int8_t *sigma, int64_t B, void *theta_out);
 
 // ---------------------------------------------------------------------------------------------- geometry
 struct TcGeom {
@@ -294,6 +296,7 @@ int theta_gemm(cudaStream_t stream, const nk_rbm_t &rbm, const int8_t *sigma, in
     return NK_EINVAL;
   }
   TcGeom g;
+  if (theta_dmma_supported(rbm)) return theta_dmma(stream, rbm, sigma, B, theta_out);  // fp64: DMMA
   if (!tc_geometry(rbm, &g)) return rbm_logpsi(stream, rbm, sigma, B, workspace, theta_out);
   uint16_t *img = reinterpret_cast<uint16_t *>(workspace);
   {

@@ -495,3 +495,28 @@ def test_theta_gemm_tensor_core(cuda, N, M, B, bias):
     got = theta.cpu().numpy()
     assert np.isfinite(got).all()
     np.testing.assert_allclose(got, ref, rtol=2e-6, atol=2e-6 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("N,M,B,bias", [(100, 400, 1000, True), (100, 400, 65, False), (20, 20, 300, True), (22, 44, 128, True),
+                                         (37, 113, 129, True), (7, 5, 3, True), (144, 576, 257, True), (250, 64, 200, True)])
+def test_theta_gemm_dmma_fp64(cuda, N, M, B, bias):
+    """nk_theta_gemm in fp64 (DMMA m8n8k4 on the FP64 tensor cores) vs the oracle's theta: 1e-13, any row / column / K tail."""
+    import ctypes as C
+
+    from netket_b200 import _lib
+
+    rs = np.random.default_rng(7)
+    W = rs.normal(size=(N, M)) * 0.3
+    b = rs.normal(size=M) if bias else None
+    sig = _sigma(B, N, seed=2)
+    Wt, st = torch.from_numpy(W).cuda(), torch.from_numpy(sig).cuda()
+    bt = torch.from_numpy(b).cuda() if bias else None
+    rbm = _lib.nk_rbm_t(W=Wt.data_ptr(), b=bt.data_ptr() if bias else None, a=None, N=N, M=M, dtype=1, reserved=0)
+    L = _lib.lib()
+    ws = torch.empty(max(1, int(L.nk_theta_gemm_workspace_bytes(C.byref(rbm), B))), dtype=torch.uint8, device="cuda")
+    theta = torch.full((B, M), float("nan"), dtype=torch.float64, device="cuda")
+    _lib.check(L.nk_theta_gemm(_lib.stream_ptr(), C.byref(rbm), _lib.ptr(st), B, _lib.ptr(theta), _lib.ptr(ws)))
+    ref = orbm.theta(sig, W, b)
+    got = theta.cpu().numpy()
+    assert np.isfinite(got).all()
+    np.testing.assert_allclose(got, ref, rtol=1e-13, atol=1e-13 * np.abs(ref).max())
