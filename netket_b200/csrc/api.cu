@@ -1,5 +1,6 @@
 // extern "C" entry points of libnkb200 (see include/nkb200.h): argument validation, path selection, launches.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -55,6 +56,9 @@ int theta_gemm(cudaStream_t stream, const nk_rbm_t &rbm, const int8_t *sigma, in
 int forces_sums(cudaStream_t stream, const nk_rbm_t &rbm, const int8_t *sigma, const void *theta, const void *eloc, int32_t eloc_dtype,
                 int64_t Ns, double mean, double *sums);
 int forces_finalize(cudaStream_t stream, const double *sums, double scale, int64_t n, void *out, int32_t dtype);
+bool forces_tc_supported(const nk_rbm_t &rbm);
+int forces_tc_sums(cudaStream_t stream, const nk_rbm_t &rbm, const int8_t *sigma, const void *theta, const void *eloc, int32_t eloc_dtype,
+                   int64_t Ns, double mean, double *sums);
 
 static int check_rbm(const nk_rbm_t *rbm, const char *who) {
   NK_CHECK_ARG(rbm != nullptr, "%s: rbm is NULL", who);
@@ -330,6 +334,9 @@ int nk_forces_rbm(void *stream, const nk_rbm_t *rbm, const int8_t *samples, int6
   void *scratch = reinterpret_cast<char *>(workspace) + ws_theta_bytes(rbm, Ns);
   rc = theta_gemm(st, *rbm, samples, Ns, theta, scratch);
   if (rc) return rc;
+  // fp32: the contraction over the samples runs on the tensor cores (forces_tc.cu); fp64 / large shapes: CUDA cores
+  if (forces_tc_supported(*rbm) && getenv("NKB200_FORCES_CUDA_CORE") == nullptr)
+    return forces_tc_sums(st, *rbm, samples, theta, eloc, eloc_dtype, Ns, mean, sums);
   return forces_sums(st, *rbm, samples, theta, eloc, eloc_dtype, Ns, mean, sums);
 }
 

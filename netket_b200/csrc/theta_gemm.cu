@@ -13,6 +13,7 @@
 //     quarter with tcgen05.ld, add the bias and store theta.
 // fp64: FP64 tensor cores (DMMA), theta_dmma.cu.  Shapes outside both kernels' limits: the CUDA-core kernel rbm_logpsi_kernel.
 #include "kernels.cuh"
+#include "tc_common.cuh"
 
 namespace nk {
 
@@ -49,26 +50,6 @@ static bool tc_geometry(const nk_rbm_t &rbm, TcGeom *g) {
   return g->smem_bytes <= 220 * 1024 && g->img_bytes < (1u << 20);
 }
 
-// ---------------------------------------------------------------------------------------------- PTX helpers
-__device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  // tcgen05 shared-memory matrix descriptor, SWIZZLE_NONE: [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version = 1
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
-}
-
-__device__ __forceinline__ uint16_t f32_to_bf16_rn(float x) {
-  uint32_t u = __float_as_uint(x);
-  u += 0x7FFFu + ((u >> 16) & 1u);  // round to nearest even (inputs are finite)
-  return (uint16_t)(u >> 16);
-}
-__device__ __forceinline__ float bf16_to_f32(uint16_t h) { return __uint_as_float((uint32_t)h << 16); }
-
 // ---------------------------------------------------------------------------------------------- prep: W -> 3 bf16 images
 // image[tile][part][(n / 8) * sbo + (k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2],  n = column inside the tile, k = site
 __global__ void theta_prep_kernel(const float *__restrict__ W, int N, int M, int kpad, int nt, int NT, int sbo, uint16_t *__restrict__ img) {
@@ -103,26 +84,6 @@ struct TcArgs {
   int N, M, kpad, nt, NT, sbo, tmem_cols, acc_cols, vec_ok;
   uint32_t part_bytes, img_bytes;
 };
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
 
 __global__ void __launch_bounds__(128, 1) theta_tc_kernel(const __grid_constant__ TcArgs p) {
   extern __shared__ __align__(1024) unsigned char smem[];
