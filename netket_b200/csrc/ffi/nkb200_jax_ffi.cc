@@ -115,3 +115,53 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(NkRbmLogPsi, LogPsiImpl,
                                   .Arg<ffi::AnyBuffer>()
                                   .Arg<ffi::Buffer<ffi::S8>>()
                                   .Ret<ffi::AnyBuffer>());
+
+// E_loc = local_value_kernel for (RBM, Ising) on given configurations (stand-alone local estimator, seam S4)
+static ffi::Error ElocIsingImpl(cudaStream_t stream, ffi::AnyBuffer W, ffi::AnyBuffer b, ffi::AnyBuffer a, ffi::Buffer<ffi::S8> sigma,
+                                ffi::Buffer<ffi::S32> edges, ffi::Result<ffi::AnyBuffer> eloc, ffi::Result<ffi::Buffer<ffi::U8>> workspace,
+                                double h, double J) {
+  const auto d = sigma.dimensions();
+  nk_rbm_t rbm{W.untyped_data(), b.untyped_data(), a.untyped_data(), (int32_t)d[1], (int32_t)W.dimensions()[1],
+               dtype_code(W.element_type()), 0};
+  nk_ising_t op{edges.typed_data(), (int32_t)edges.dimensions()[0], 0, h, J};
+  const int rc = nk_eloc_ising_rbm(stream, &rbm, &op, sigma.typed_data(), d[0], eloc->untyped_data(), dtype_code(eloc->element_type()),
+                                   NK_PATH_AUTO, workspace->typed_data());
+  return rc == NK_OK ? ffi::Error::Success() : fail();
+}
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(NkElocIsing, ElocIsingImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::AnyBuffer>()          // W
+                                  .Arg<ffi::AnyBuffer>()          // b
+                                  .Arg<ffi::AnyBuffer>()          // a
+                                  .Arg<ffi::Buffer<ffi::S8>>()    // sigma (B, N)
+                                  .Arg<ffi::Buffer<ffi::S32>>()   // edges (E, 2)
+                                  .Ret<ffi::AnyBuffer>()          // E_loc (B,)
+                                  .Ret<ffi::Buffer<ffi::U8>>()    // workspace (nk_sweep_workspace_bytes)
+                                  .Attr<double>("h")
+                                  .Attr<double>("J"));
+
+// sums[N*M + M + N] = sum_s dlogpsi(sigma_s) * (eloc_s - mean)   (forces before the cross-device psum and the 1/n scale)
+static ffi::Error ForcesImpl(cudaStream_t stream, ffi::AnyBuffer W, ffi::AnyBuffer b, ffi::AnyBuffer a, ffi::Buffer<ffi::S8> samples,
+                             ffi::AnyBuffer eloc, ffi::Result<ffi::Buffer<ffi::F64>> sums, ffi::Result<ffi::Buffer<ffi::U8>> workspace,
+                             double mean) {
+  const auto d = samples.dimensions();
+  nk_rbm_t rbm{W.untyped_data(), b.untyped_data(), a.untyped_data(), (int32_t)d[1], (int32_t)W.dimensions()[1],
+               dtype_code(W.element_type()), 0};
+  const int rc = nk_forces_rbm(stream, &rbm, samples.typed_data(), d[0], eloc.untyped_data(), dtype_code(eloc.element_type()), mean,
+                               sums->typed_data(), workspace->typed_data());
+  return rc == NK_OK ? ffi::Error::Success() : fail();
+}
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(NkForces, ForcesImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::AnyBuffer>()          // W
+                                  .Arg<ffi::AnyBuffer>()          // b
+                                  .Arg<ffi::AnyBuffer>()          // a
+                                  .Arg<ffi::Buffer<ffi::S8>>()    // samples (n_s, N)
+                                  .Arg<ffi::AnyBuffer>()          // E_loc (n_s,)
+                                  .Ret<ffi::Buffer<ffi::F64>>()   // sums
+                                  .Ret<ffi::Buffer<ffi::U8>>()    // workspace (nk_forces_workspace_bytes)
+                                  .Attr<double>("mean"));
