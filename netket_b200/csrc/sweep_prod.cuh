@@ -695,7 +695,41 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
           if (e < E) zz += 1 - 2 * par;
         }
         dl = s.ising.J * (double)zz;
-        rounds0 = s.ising.h != 0.0 ? (N + 31) / 32 : 0;
+        rounds0 = 0;
+        // the N single flips are a static candidate list: no descriptors to shuffle.  NB sites at a time, spins from one
+        // ballot per 32 sites, NB independent lane products, then the transposed butterfly.
+        if (s.ising.h != 0.0) {
+          const T mel = (T)(-s.ising.h);
+          uint32_t word = 0;
+          for (int base = 0; base < N; base += NB) {
+            if ((base & 31) == 0) word = __ballot_sync(FULL, (mybits >> (base >> 5)) & 1u);
+            const uint32_t bits = word >> (base & 31);
+            T v[NB];
+#pragma unroll
+            for (int jj = 0; jj < NB; ++jj) {
+              v[jj] = F64 ? T(1) : T(0);
+              const int site = base + jj;
+              if (site < N) {
+                V g[NV];
+                fetch(site, g);
+                const T P = ((bits >> jj) & 1u) ? lane_product<V, NV>(Bv, A, g) : lane_product<V, NV>(A, Bv, g);
+                if constexpr (F64)
+                  v[jj] = P;
+                else
+                  v[jj] = lg2_fast(P);
+              }
+            }
+            const T tot = gcomb(bfly<T, NB>(v, lane), [&](T x, T y) { return bf_op(x, y); });
+            const int mys = base + myidx;
+            if ((lane & 1) == 0 && lane < 2 * NB && mys < N) {
+              const bool pos = (bits >> myidx) & 1u;
+              if constexpr (F64)
+                off_l += mel * (tot * (pos ? rctab[mys].ep : rctab[mys].em) / nrm);
+              else
+                off_l += mel * ex2_fast(tot - nrm + (pos ? rctab[mys].x2 + rctab[mys].y2 : rctab[mys].x2 - rctab[mys].y2));
+            }
+          }
+        }
       } else {
         // LocalOperator: diagonal = constant + sum_terms diag_mels[row]; off-diagonal entries with |mel| > cutoff
         // (_local_operator/jax.py:104-199; the compaction only reorders, the sum runs over the same entries)
