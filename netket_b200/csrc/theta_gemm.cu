@@ -208,8 +208,22 @@ __global__ void __launch_bounds__(128, 1) theta_tc_kernel(const __grid_constant_
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (row < p.B) {
           const int jbase = n0 + c0;
-          if (p.vec_ok && jbase + width <= p.M) {
-            // 128-bit stores: this thread owns `width` consecutive floats of its row
+          if (p.vec_ok == 2 && jbase + width <= p.M) {
+            // 256-bit stores (sm_100): this thread owns `width` consecutive floats of its row and writes whole 32-byte
+            // sectors, so that no partial-sector writes reach L2
+#pragma unroll
+            for (int e = 0; e < 32; e += 8) {
+              if (e < width) {
+                float v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(r[e + q]) + (p.bias != nullptr ? p.bias[jbase + e + q] : 0.0f);
+                asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(out + jbase + e), "f"(v[0]), "f"(v[1]),
+                             "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                             : "memory");
+              }
+            }
+          } else if (p.vec_ok && jbase + width <= p.M) {
+            // 128-bit stores
 #pragma unroll
             for (int e = 0; e < 32; e += 4) {
               if (e < width) {
@@ -282,6 +296,8 @@ int theta_gemm(cudaStream_t stream, const nk_rbm_t &rbm, const int8_t *sigma, in
   a.acc_cols = g.acc_cols;
   a.vec_ok = (rbm.M % 4 == 0) && ((reinterpret_cast<uintptr_t>(theta_out) & 15) == 0) &&
              (rbm.b == nullptr || (reinterpret_cast<uintptr_t>(rbm.b) & 15) == 0);
+  // 256-bit stores need 32-byte aligned rows, tiles and 16-column chunks (NT is a multiple of 16: chunk widths are 32 or 16)
+  if (a.vec_ok && rbm.M % 8 == 0 && g.NT % 8 == 0 && (reinterpret_cast<uintptr_t>(theta_out) & 31) == 0) a.vec_ok = 2;
   a.part_bytes = (uint32_t)g.part_bytes;
   a.img_bytes = (uint32_t)g.img_bytes;
   NK_CUDA_OK(cudaFuncSetAttribute(theta_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
