@@ -224,7 +224,12 @@ def measure(nk, torch, dist, rank, ws, device, dtype, steps, warmup):
     kernel = ("sweep_fast_kernel<3,1> (fused sweep + E_loc, fp32 LocalRule specialisation)" if dtype == "float32"
               else "sweep_prod_kernel<double,6,1,LocalRule> (fused sweep + E_loc; 66 of 100 table rows resident in shared memory, "
                    "the others read through L2)")
-    roofline = {"bound": "smem", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    # DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture (dram__bytes_read.sum +
+    # dram__bytes_write.sum; profiles/r01_fast_f32_ncu_raw.csv, r01_prod_f64_ncu_raw.csv): theta in, samples + E_loc out.
+    traffic = 184.4e6 if dtype == "float32" else 310.4e6
+    roofline = {"bound": "smem", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_note": "HBM bytes per launch from the committed ncu capture of the same workload (not re-measured by bench.py); "
+                                "the roofline above counts on-chip operand bytes, of which this is 0.05 %",
                 "kernel": kernel, "kernel_ms": ms_kernel, "theta_kernel_ms": ms_theta,
                 "algorithmic_bytes_per_sample": bytes_per_sample(esz),
                 "peak_source": "measured in this run by nk_microbench(0) (LDS.128 shared-memory read bandwidth, all SMs); "
