@@ -226,7 +226,7 @@ def measure(nk, torch, dist, rank, ws, device, dtype, steps, warmup):
                    "the others read through L2)")
     # DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture (dram__bytes_read.sum +
     # dram__bytes_write.sum; profiles/r01_fast_f32_ncu_raw.csv, r01_prod_f64_ncu_raw.csv): theta in, samples + E_loc out.
-    traffic = 184.4e6 if dtype == "float32" else 310.4e6
+    traffic = 184.4e6 if dtype == "float32" else 311.1e6
     roofline = {"bound": "smem", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_note": "HBM bytes per launch from the committed ncu capture of the same workload (not re-measured by bench.py); "
                                 "the roofline above counts on-chip operand bytes, of which this is 0.05 %",
