@@ -4,7 +4,7 @@
 // which stays the path for fp64 and for shapes outside this kernel's limits).
 //
 // It is a (N x n_s)(n_s x M) GEMM whose reduction dimension is the sample index.  A CTA owns a tile of NT hidden units and
-// streams over its share of the samples 128 at a time; per block of samples its 256 threads write two K-major operand
+// streams over its share of the samples 128 at a time; per block of samples its 512 threads write two K-major operand
 // tiles straight into shared memory in the tcgen05 core-matrix layout:
 //     A'[i, s] = sigma[s, i]      (exact in bf16; row N is all ones, so that D[N, j] = sum_s x[s, j] = F_b[j])
 //     B'[j, s] = x[s, j]          split exactly into three bf16 parts (three tiles); column NT holds w[s] = E_loc[s] - mean,
@@ -34,7 +34,9 @@ struct FtcArgs {
   double *sums;
 };
 
-__global__ void __launch_bounds__(256, 1) forces_tc_kernel(const __grid_constant__ FtcArgs p) {
+constexpr int FT_THREADS = 512;  // 16 warps: one group of 8 samples each per block (more theta loads in flight)
+
+__global__ void __launch_bounds__(FT_THREADS, 1) forces_tc_kernel(const __grid_constant__ FtcArgs p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char *a_tile = smem;                                   // 128 x 128 bf16
   const uint32_t b_part_bytes = (uint32_t)(p.NTX / 8) * FT_SBO;   // one bf16 part of B'
@@ -74,7 +76,7 @@ __global__ void __launch_bounds__(256, 1) forces_tc_kernel(const __grid_constant
       mma_phase ^= 1u;
     }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    for (int g = warp; g < FT_KS / 8; g += 8) {
+    for (int g = warp; g < FT_KS / 8; g += FT_THREADS / 32) {
       const int64_t s0 = blk * FT_KS + 8 * g;
       // w[q] = E_loc[s0 + q] - mean for the 8 samples of the group (lane q < 8 loads, everyone gets all 8 by shuffle)
       float wl = 0.0f;
@@ -250,7 +252,7 @@ int forces_tc_sums(cudaStream_t stream, const nk_rbm_t &rbm, const int8_t *sigma
   int64_t ctas = (int64_t)(num_sms() / g.nt) * g.nt;
   if (ctas < g.nt) ctas = g.nt;
   if (ctas > n_blocks * g.nt) ctas = n_blocks * g.nt;
-  forces_tc_kernel<<<(int)ctas, 256, g.smem, stream>>>(a);
+  forces_tc_kernel<<<(int)ctas, FT_THREADS, g.smem, stream>>>(a);
   NK_LAUNCH_OK();
   return NK_OK;
 }
