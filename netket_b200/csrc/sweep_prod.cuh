@@ -683,7 +683,7 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
         nrm = gcomb(warp_sum(lg2_fast(lane_norm())), op_add);
       T off_l = T(0);
       double dl = 0.0;  // diagonal, per-lane partial
-      // candidates are produced 32 at a time (one per lane); rounds enumerate sites (Ising) or (term, entry) slots
+      // LocalOperator candidates are produced 32 at a time (one per lane); rounds enumerate the (term, entry) slots
       int rounds0, rounds1 = 0;
       if (s.eloc_kind == 1) {
         // E_loc = J sum_<ij> s_i s_j - h sum_i psi(sigma^(i)) / psi(sigma)        (_ising/jax.py:125-165)
@@ -741,12 +741,7 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
       for (int r = 0; r < rounds0 + rounds1; ++r) {
         uint32_t d = 0;
         T mel = T(0);
-        if (s.eloc_kind == 1) {
-          const int site = 32 * r + lane;
-          const uint32_t sb = sbit(site < N ? site : 0);
-          if (site < N) d = CD_VALID | CD_CHG0 | (uint32_t)site | ((uint32_t)site << CD_S1_SHIFT) | (sb ? CD_POS0 : 0u);
-          mel = (T)(-s.ising.h);
-        } else {
+        {  // LocalOperator only: the Ising candidates were handled above (rounds0 = rounds1 = 0)
           const int gi = r < rounds0 ? 0 : 1;
           const nk_localop_group_t &G = s.localop.groups[gi];
           const int rows = 1 << G.n_sites, ncm = G.ncmax;
@@ -781,10 +776,8 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
           }
         }
         eval_round(std::integral_constant<int, 0>{}, d, mel, nrm, off_l);
-        if (s.eloc_kind == 2) {
-          eval_round(std::integral_constant<int, 1>{}, d, mel, nrm, off_l);
-          eval_round(std::integral_constant<int, 2>{}, d, mel, nrm, off_l);
-        }
+        eval_round(std::integral_constant<int, 1>{}, d, mel, nrm, off_l);
+        eval_round(std::integral_constant<int, 2>{}, d, mel, nrm, off_l);
       }
       const double diag = warp_sum(dl) + (s.eloc_kind == 2 ? s.localop.constant : 0.0);
       T acc = warp_sum(off_l);
