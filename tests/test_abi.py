@@ -78,6 +78,22 @@ def test_argument_validation_happens_before_cuda(lib_built):
     assert L.nk_localop_conn(None, C.byref(op), None, 1, 4, None, None, 1, None) == -1
     assert b"supported: 1, 2" in L.nk_last_error()
     assert L.nk_sweep_workspace_bytes(C.byref(rbm), 10) > 0
+    # entry points added for the stand-alone estimator and the forces: argument validation happens before any CUDA call
+    a.rule, a.path = 0, 7
+    assert L.nk_sweep(None, C.byref(rbm), C.byref(ch), C.byref(a)) == -1
+    assert b"bad path" in L.nk_last_error()
+    ising = _lib.nk_ising_t(edges=None, n_edges=0, reserved=0, h=1.0, J=1.0)
+    assert L.nk_eloc_ising_rbm(None, C.byref(rbm), C.byref(ising), 1, 2, 1, 5, 0, None) == -1
+    assert b"eloc_dtype" in L.nk_last_error()
+    assert L.nk_eloc_ising_rbm(None, C.byref(rbm), C.byref(ising), 1, 2, 1, 1, 9, None) == -1
+    assert b"bad path" in L.nk_last_error()
+    assert L.nk_forces_rbm(None, C.byref(rbm), 1, 4, 1, 1, 0.0, None, 1) == -1
+    assert L.nk_forces_rbm(None, C.byref(rbm), None, 4, 1, 1, 0.0, 1, 1) == -1
+    assert b"NULL buffer" in L.nk_last_error()
+    assert L.nk_forces_finalize(None, None, 1.0, 4, None, 0) == -1
+    assert L.nk_forces_workspace_bytes(C.byref(rbm), 1000) >= 1000 * 4 * 4
+    big = _lib.nk_rbm_t(W=1, b=None, a=None, N=400, M=3200, dtype=0, reserved=0)
+    assert L.nk_sweep_workspace_bytes(C.byref(big), 8) >= 8 * 3200 * 4 + 400 * 3200 * 4  # theta + the G table (several warps per chain)
 
 
 def _partials(x, mu):
