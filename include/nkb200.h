@@ -44,7 +44,8 @@ extern "C" {
 /* kernel-path selection for the sweep / E_loc kernels (NK_PATH_AUTO picks the fastest valid one) */
 #define NK_PATH_AUTO 0
 #define NK_PATH_GENERIC 1 /* theta-form, lncosh differences; any shape, any |W| */
-#define NK_PATH_FAST 2    /* product form on exp(-4W) tables resident in shared memory; error if no such kernel applies */
+#define NK_PATH_FAST 2    /* product form on exp(-4W) tables; error if no such kernel covers the configuration (weights outside
+                             the form's numerical range still hand over, in-stream, to the theta-form kernel) */
 #define NK_PATH_PROD 3    /* like NK_PATH_FAST, but always the general product-form kernel (fp32/fp64, both rules) */
 
 typedef struct nk_rbm_t {

@@ -210,8 +210,10 @@ int nk_sweep(void *stream, const nk_rbm_t *rbm, nk_chains_t *ch, const nk_sweep_
     rc = theta_gemm(st, *rbm, ch->sigma, ch->B, theta, scratch);  // theta = sigma W + b  (the only dense contraction)
     if (rc) return rc;
     rc = fast_ok ? sweep_fast(st, k, reinterpret_cast<const float *>(theta), flags) : sweep_prod(st, k, theta, flags, tables);
-    if (rc == NK_OK && a->path == NK_PATH_AUTO) {
-      // weights beyond the product form's range: the kernel raises flags[0] and exits; this one then runs
+    if (rc == NK_OK) {
+      // weights beyond the product form's range (a property of the data, found by the prep kernels): the product kernel
+      // raises flags[0] and exits; this one then runs.  Also enqueued when the path was forced, so that a forced path can
+      // never return without having produced its outputs.
       k.run_if_flag = flags;
       rc = sweep_generic(st, k);
     }
@@ -288,7 +290,7 @@ static int eloc_dispatch(cudaStream_t st, const nk_rbm_t *rbm, const nk_ising_t 
   int rc = theta_gemm(st, *rbm, sigma, B, theta, scratch);
   if (rc) return rc;
   rc = sweep_prod(st, k, theta, flags, tables);
-  if (rc == NK_OK && path == NK_PATH_AUTO) rc = eloc_generic(st, *rbm, ising, localop, sigma, B, eloc_out, eloc_dtype, flags);
+  if (rc == NK_OK) rc = eloc_generic(st, *rbm, ising, localop, sigma, B, eloc_out, eloc_dtype, flags);  // in-stream hand-over
   return rc;
 }
 

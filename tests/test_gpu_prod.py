@@ -376,3 +376,70 @@ def test_prod_large_fused_eloc(cuda, dtype, rule, L, n_dim, alpha, std, total_sz
     vs = nk.vqs.MCState(sa, model, variables=var, n_samples=B, seed=1)
     alone = vs._eloc_on_samples(op, samples, path=PROD)
     np.testing.assert_allclose(alone.cpu().numpy(), ref, rtol=tol, atol=tol * np.abs(ref).max())
+
+
+# ----------------------------------------------------------------------------------------- edge shapes
+@pytest.mark.parametrize("N,M,B,CL,sweep_size", [(2, 1, 1, 3, None), (3, 5, 7, 2, 1), (128, 128, 5, 1, None), (129, 64, 3, 1, 40),
+                                                  (16, 512, 9, 2, None), (16, 513, 9, 2, None), (31, 33, 33, 2, 100), (64, 65, 4, 1, None)])
+def test_prod_edge_shapes_fp64(cuda, N, M, B, CL, sweep_size):
+    """Smallest / boundary shapes of the product-form kernels (one chain, one hidden unit, N = 128 / 129, M = 512 / 513,
+    sweep_size of 1 and larger than N): fp64 chains, log-probabilities and fused E_loc against the oracle."""
+    nk = _nk()
+    rs = np.random.default_rng(N * 1000 + M)
+    std = 0.2 if M < 512 else 0.04  # (16 hidden units per lane: larger weights leave the product form's range)
+    W = rs.normal(size=(N, M)) * std
+    b = rs.normal(size=M) * 0.2
+    a = rs.normal(size=N) * 0.2
+    var = {"params": {"Dense": {"kernel": torch.from_numpy(W).cuda(), "bias": torch.from_numpy(b).cuda()},
+                      "visible_bias": torch.from_numpy(a).cuda()}}
+    g = nk.graph.Hypercube(N, 1, pbc=N > 2)
+    hi = nk.hilbert.Spin(0.5, N)
+    op = nk.operator.Ising(hi, g, h=0.7)
+    model = nk.models.RBM(alpha=M / N)
+    assert model.n_hidden(N) == M
+    sa = nk.sampler.MetropolisLocal(hi, n_chains=B, sweep_size=sweep_size)
+    st = sa.init_state(model, var, seed=5)
+    seed, t0 = st.rng
+    ref = osampler.sample_chain("local", st.σ.cpu().numpy(), W, b, a, chain_length=CL, sweep_size=sweep_size, seed=seed, t0=t0)
+    samples, logp, eloc, st2 = sa._launch(model, var, st, CL, operator=op, return_log_probabilities=True, path=PROD)
+    assert np.array_equal(samples.cpu().numpy(), ref["samples"])
+    np.testing.assert_allclose(logp.cpu().numpy(), ref["log_prob_samples"], rtol=1e-10, atol=1e-10)
+    assert np.array_equal(st2.n_accepted_proc.cpu().numpy(), ref["n_accepted"])
+    e = np.asarray(g.edges(), dtype=np.int64).reshape(-1, 2)
+    eref = oest.local_estimators(ref["samples"], lambda x: oops.ising_conn_padded(x, e, 0.7, 1.0), W, b, a)
+    np.testing.assert_allclose(eloc.cpu().numpy(), eref, rtol=1e-11, atol=1e-11 * max(1.0, np.abs(eref).max()))
+
+
+def test_prod_burn_in_only_and_empty_batch(cuda):
+    """chain_length = 0 (pure burn-in) advances the chains exactly like the first sweeps of a longer run; B = 0 is a no-op."""
+    nk = _nk()
+    g, hi, (W, b, a), var, model, sa, _, e, col = _case(nk, "local", 12, 1, 2, np.float64, 0.3, 6)
+    st = sa.init_state(model, var, seed=8)
+    seed, t0 = st.rng
+    ref = osampler.sample_chain("local", st.σ.cpu().numpy(), W, b, a, chain_length=3, seed=seed, t0=t0)
+    samples, _, _, st2 = sa._launch(model, var, st, 0, n_discard=3, path=PROD)
+    assert tuple(samples.shape) == (6, 0, 12)
+    assert np.array_equal(st2.σ.cpu().numpy(), ref["sigma"])
+    assert st2.rng == (seed, ref["t"])
+    import ctypes as C
+
+    from netket_b200 import _lib
+
+    rbm = nk.models.RBM.c_struct(var)
+    ch = _lib.nk_chains_t(sigma=None, log_prob=None, n_accepted=None, workspace=None, B=0, seed=0, t=0, chain_offset=0)
+    args = _lib.nk_sweep_t()
+    args.rule, args.chain_length, args.n_discard, args.sweep_size, args.machine_pow, args.path = 0, 1, 0, 12, 2.0, 0
+    assert _lib.lib().nk_sweep(_lib.stream_ptr(), C.byref(rbm), C.byref(ch), C.byref(args)) == 0
+
+
+def test_forced_product_path_still_produces_outputs_for_large_weights(cuda):
+    """NK_PATH_PROD with weights outside the product form's numerical range: the in-stream hand-over runs all the same."""
+    nk = _nk()
+    g, hi, (W, b, a), var, model, sa, _, e, col = _case(nk, "local", 4, 2, 16, np.float64, 1.5, 16)
+    op = nk.operator.Ising(hi, g, h=1.0)
+    st = sa.init_state(model, var, seed=3)
+    s_prod, _, e_prod, _ = sa._launch(model, var, st, 3, operator=op, path=PROD)
+    s_gen, _, e_gen, _ = sa._launch(model, var, st, 3, operator=op, path=1)
+    assert np.array_equal(s_prod.cpu().numpy(), s_gen.cpu().numpy())
+    assert np.array_equal(e_prod.cpu().numpy(), e_gen.cpu().numpy())
+    assert set(np.unique(s_prod.cpu().numpy())) <= {-1, 1}
