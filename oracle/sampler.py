@@ -55,7 +55,9 @@ def _propose_exchange(sigma, w0, clusters):
     n_hop_p = hoppable_mask(sp, clusters).sum(axis=1)
     with np.errstate(divide="ignore", invalid="ignore"):
         corr = np.log(n_hop.astype(np.float64)) - np.log(n_hop_p.astype(np.float64))
-    corr = np.where(ok, corr, 0.0)
+    # no hoppable cluster: the reference's correction is log(0) - log(0) = nan (rules/exchange.py:177-182), so that
+    # `u < exp(nan)` is False: the (identity) proposal is rejected and not counted as accepted
+    corr = np.where(ok, corr, np.nan)
     return sp, corr, sel
 
 
@@ -121,7 +123,7 @@ def sample_chain(
             arg = logp_p - logp
             if corr is not None:
                 arg = arg + corr.astype(dtype)
-            with np.errstate(over="ignore"):
+            with np.errstate(over="ignore", invalid="ignore"):
                 acc = u[t] < np.exp(arg)
             sigma = np.where(acc[:, None], sp, sigma)
             logp = np.where(acc, logp_p, logp)

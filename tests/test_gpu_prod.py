@@ -443,3 +443,58 @@ def test_forced_product_path_still_produces_outputs_for_large_weights(cuda):
     assert np.array_equal(s_prod.cpu().numpy(), s_gen.cpu().numpy())
     assert np.array_equal(e_prod.cpu().numpy(), e_gen.cpu().numpy())
     assert set(np.unique(s_prod.cpu().numpy())) <= {-1, 1}
+
+
+# ----------------------------------------------------------------------------------------- exchange-rule edge cases
+@pytest.mark.parametrize("L,n_dim,d_max,total_sz,expect_clusters", [(10, 2, 3, 0, 1200),     # > 1024 clusters: second hop word per lane
+                                                                     (6, 2, 6, 0, 630),       # all pairs: 35 clusters per site > 32 -> hand-over
+                                                                     (8, 1, 1, 4, 8),         # all spins up: no hoppable cluster, chains frozen
+                                                                     (4, 1, 1, 0, 4)])
+def test_prod_exchange_edge_cases_fp64(cuda, L, n_dim, d_max, total_sz, expect_clusters):
+    nk = _nk()
+    B, CL = 6, 2
+    g, hi, (W, b, a), var, model, sa, clusters, e, col = _case(nk, "exchange", L, n_dim, 2, np.float64, 0.1, B, total_sz, d_max)
+    assert clusters.shape[0] == expect_clusters
+    st = sa.init_state(model, var, seed=21)
+    seed, t0 = st.rng
+    ref = osampler.sample_chain("exchange", st.σ.cpu().numpy(), W, b, a, chain_length=CL, seed=seed, t0=t0, clusters=clusters)
+    for path in (PROD, 1):  # product-form and theta-form kernels
+        (samples, logp), st2 = sa.sample(model, var, state=st, chain_length=CL, return_log_probabilities=True, _path=path)
+        assert np.array_equal(samples.cpu().numpy(), ref["samples"])
+        np.testing.assert_allclose(logp.cpu().numpy(), ref["log_prob_samples"], rtol=1e-10, atol=1e-10)
+        assert np.array_equal(st2.n_accepted_proc.cpu().numpy(), ref["n_accepted"])
+        if total_sz == L ** n_dim / 2:  # no hoppable cluster: the reference's nan correction rejects every (identity) proposal
+            assert int(st2.n_accepted_proc.sum()) == 0 and np.array_equal(st2.σ.cpu().numpy(), st.σ.cpu().numpy())
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("hb,vb", [(False, True), (True, False), (False, False)])
+def test_prod_without_biases(cuda, dtype, hb, vb):
+    nk = _nk()
+    N, alpha, B = 12, 3, 10
+    W, b, a = orbm.init_params(N, alpha, seed=3, std=0.2, dtype=dtype, use_hidden_bias=hb, use_visible_bias=vb)
+    dense = {"kernel": torch.from_numpy(W).cuda()}
+    if hb:
+        dense["bias"] = torch.from_numpy(b).cuda()
+    p = {"Dense": dense}
+    if vb:
+        p["visible_bias"] = torch.from_numpy(a).cuda()
+    var = {"params": p}
+    g = nk.graph.Hypercube(N, 1)
+    hi = nk.hilbert.Spin(0.5, N)
+    op = nk.operator.Ising(hi, g, h=1.1)
+    model = nk.models.RBM(alpha=alpha, param_dtype=dtype, use_hidden_bias=hb, use_visible_bias=vb)
+    sa = nk.sampler.MetropolisLocal(hi, n_chains=B)
+    st = sa.init_state(model, var, seed=2)
+    samples, _, eloc, _ = sa._launch(model, var, st, 3, operator=op, path=PROD)
+    e, _ = ograph.hypercube_edges(N, 1)
+    W64 = W.astype(np.float64)
+    b64 = None if b is None else b.astype(np.float64)
+    a64 = None if a is None else a.astype(np.float64)
+    ref = oest.local_estimators(samples.cpu().numpy(), lambda x: oops.ising_conn_padded(x, e, 1.1, 1.0), W64, b64, a64)
+    tol = 1e-11 if dtype == np.float64 else 1e-5
+    np.testing.assert_allclose(eloc.cpu().numpy(), ref, rtol=tol, atol=tol * np.abs(ref).max())
+    if dtype == np.float64:
+        seed, t0 = st.rng
+        r = osampler.sample_chain("local", st.σ.cpu().numpy(), W64, b64, a64, chain_length=3, seed=seed, t0=t0)
+        assert np.array_equal(samples.cpu().numpy(), r["samples"])
