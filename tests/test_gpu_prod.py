@@ -498,3 +498,85 @@ def test_prod_without_biases(cuda, dtype, hb, vb):
         seed, t0 = st.rng
         r = osampler.sample_chain("local", st.σ.cpu().numpy(), W64, b64, a64, chain_length=3, seed=seed, t0=t0)
         assert np.array_equal(samples.cpu().numpy(), r["samples"])
+
+
+# ----------------------------------------------------------------------------------------- more sampler / operator edge cases
+@pytest.mark.parametrize("rule,machine_pow", [("local", 1.0), ("local", 3.0), ("local", 0.5), ("exchange", 1.0), ("exchange", 2.5),
+                                              ("local", 0.0)])
+def test_prod_machine_pow_fp64(cuda, rule, machine_pow):
+    """sampler/base.py:139-150: machine_pow is any non-negative real; 0 samples the uniform distribution (always accept)."""
+    nk = _nk()
+    N, B = 12, 10
+    g = nk.graph.Hypercube(N, 1)
+    total_sz = 0 if rule == "exchange" else None
+    hi = nk.hilbert.Spin(0.5, N, total_sz=total_sz)
+    (W, b, a), var = _params(N, 2, np.float64, 0.4)
+    model = nk.models.RBM(alpha=2)
+    e, _ = ograph.hypercube_edges(N, 1)
+    if rule == "local":
+        sa, clusters = nk.sampler.MetropolisLocal(hi, n_chains=B, machine_pow=machine_pow), None
+    else:
+        sa = nk.sampler.MetropolisExchange(hi, graph=g, d_max=2, n_chains=B, machine_pow=machine_pow)
+        clusters = ograph.compute_clusters(N, e, 2)
+    st = sa.init_state(model, var, seed=17)
+    seed, t0 = st.rng
+    ref = osampler.sample_chain(rule, st.σ.cpu().numpy(), W, b, a, chain_length=3, seed=seed, t0=t0, clusters=clusters,
+                                machine_pow=machine_pow)
+    for path in (PROD, 1):
+        (samples, logp), st2 = sa.sample(model, var, state=st, chain_length=3, return_log_probabilities=True, _path=path)
+        assert np.array_equal(samples.cpu().numpy(), ref["samples"]), path
+        np.testing.assert_allclose(logp.cpu().numpy(), ref["log_prob_samples"], rtol=1e-10, atol=1e-10)
+        assert np.array_equal(st2.n_accepted_proc.cpu().numpy(), ref["n_accepted"])
+    if machine_pow == 0.0:
+        assert int(st2.n_accepted_proc.sum()) == B * 3 * N
+
+
+def test_prod_sharded_chains_and_large_counters(cuda):
+    """chain_offset (multi-GPU sharding) and Philox counters / seeds beyond 32 bits on the product-form kernel."""
+    nk = _nk()
+    g, hi, (W, b, a), var, model, sa, _, e, col = _case(nk, "local", 12, 1, 1, np.float64, 0.3, 12)
+    seed, t0 = (1 << 40) + 12345, (1 << 33) + 7
+    st = sa.init_state(model, var, seed=4).replace(rng=(seed, t0))
+    full, stf = sa.sample(model, var, state=st, chain_length=2, _path=PROD)
+    ref = osampler.sample_chain("local", st.σ.cpu().numpy(), W, b, a, chain_length=2, seed=seed, t0=t0)
+    assert np.array_equal(full.cpu().numpy(), ref["samples"])
+    assert stf.rng == (seed, t0 + 2 * 12)
+    sa8 = nk.sampler.MetropolisLocal(hi, n_chains=8)
+    st8 = sa8.init_state(model, var, seed=4).replace(σ=st.σ[4:12].clone(), chain_offset=4, rng=(seed, t0))
+    part, _ = sa8.sample(model, var, state=st8, chain_length=2, _path=PROD)
+    assert np.array_equal(part.cpu().numpy(), full[4:12].cpu().numpy())
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_prod_local_operator_edge_cases(cuda, dtype):
+    """1-site-only operators (a transverse field written as a LocalOperator equals Ising with J = 0), a pure constant, entries
+    below mel_cutoff, and a term given twice (summed by the reference's `_append_matrix`)."""
+    nk = _nk()
+    N, B = 10, 12
+    g = nk.graph.Hypercube(N, 1)
+    hi = nk.hilbert.Spin(0.5, N)
+    (W, b, a), var = _params(N, 2, dtype, 0.3)
+    model = nk.models.RBM(alpha=2, param_dtype=dtype)
+    sa = nk.sampler.MetropolisLocal(hi, n_chains=B)
+    st = sa.init_state(model, var, seed=6)
+    sx = np.array([[0.0, 1.0], [1.0, 0.0]])
+    sz = np.array([[1.0, 0.0], [0.0, -1.0]])
+    tol = 1e-11 if dtype == np.float64 else 2e-5
+    W64, b64, a64 = _f64(W, b, a)
+    # transverse field as LocalOperator == Ising(h, J=0)
+    op_x = nk.operator.LocalOperator(hi, [-1.3 * sx] * N, [[i] for i in range(N)])
+    samples, _, e_x, _ = sa._launch(model, var, st, 2, operator=op_x, path=PROD)
+    e, _ = ograph.hypercube_edges(N, 1)
+    ref = oest.local_estimators(samples.cpu().numpy(), lambda x: oops.ising_conn_padded(x, e, 1.3, 0.0), W64, b64, a64)
+    np.testing.assert_allclose(e_x.cpu().numpy(), ref, rtol=tol, atol=tol * np.abs(ref).max())
+    # constant + diagonal terms only, with an off-diagonal entry below the cutoff and a duplicated term
+    tiny = np.array([[0.0, 1e-12], [1e-12, 0.0]])
+    ops = [0.5 * sz, tiny, 0.5 * sz, np.kron(sz, sz)]
+    aon = [[0], [1], [0], [2, 3]]
+    op_d = nk.operator.LocalOperator(hi, ops, aon, constant=0.7)
+    tables = oops.pack_internals(oops.canonical_operators_dict(ops, aon), 0.7)
+    samples, _, e_d, _ = sa._launch(model, var, st, 2, operator=op_d, path=PROD)
+    ref = oest.local_estimators(samples.cpu().numpy(), lambda x: oops.local_operator_conn_padded(x, tables), W64, b64, a64)
+    np.testing.assert_allclose(e_d.cpu().numpy(), ref, rtol=tol, atol=tol * np.abs(ref).max())
+    s = samples.cpu().numpy().astype(np.float64)
+    np.testing.assert_allclose(e_d.cpu().numpy(), 0.7 + s[..., 0] + s[..., 2] * s[..., 3], rtol=tol, atol=tol)
