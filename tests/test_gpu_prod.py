@@ -580,3 +580,34 @@ def test_prod_local_operator_edge_cases(cuda, dtype):
     np.testing.assert_allclose(e_d.cpu().numpy(), ref, rtol=tol, atol=tol * np.abs(ref).max())
     s = samples.cpu().numpy().astype(np.float64)
     np.testing.assert_allclose(e_d.cpu().numpy(), 0.7 + s[..., 0] + s[..., 2] * s[..., 3], rtol=tol, atol=tol)
+
+
+@pytest.mark.parametrize("N,M", [(128, 256), (100, 512), (128, 512), (16, 4), (64, 500), (127, 132)])
+def test_auto_path_boundaries_fp32(cuda, N, M):
+    """NK_PATH_AUTO in fp32 at the limits of the kernels' coverage (tuned kernel: table resident, M % 4 == 0; general kernel:
+    one warp, resident; general kernel: table read through L2): fused E_loc vs oracle and the chains vs the fp64 oracle."""
+    nk = _nk()
+    B, CL = 24, 2
+    rs = np.random.default_rng(N + M)
+    W = (rs.normal(size=(N, M)) * 0.03).astype(np.float32)
+    b = (rs.normal(size=M) * 0.1).astype(np.float32)
+    a = (rs.normal(size=N) * 0.1).astype(np.float32)
+    var = {"params": {"Dense": {"kernel": torch.from_numpy(W).cuda(), "bias": torch.from_numpy(b).cuda()},
+                      "visible_bias": torch.from_numpy(a).cuda()}}
+    g = nk.graph.Hypercube(N, 1)
+    hi = nk.hilbert.Spin(0.5, N)
+    op = nk.operator.Ising(hi, g, h=1.0)
+    model = nk.models.RBM(alpha=M / N, param_dtype=np.float32)
+    assert model.n_hidden(N) == M
+    sa = nk.sampler.MetropolisLocal(hi, n_chains=B)
+    st = sa.init_state(model, var, seed=9)
+    samples, _, eloc, st2 = sa._launch(model, var, st, CL, operator=op, path=0)
+    W64, b64, a64 = _f64(W, b, a)
+    e = np.asarray(g.edges(), dtype=np.int64).reshape(-1, 2)
+    ref = oest.local_estimators(samples.cpu().numpy(), lambda x: oops.ising_conn_padded(x, e, 1.0, 1.0), W64, b64, a64)
+    np.testing.assert_allclose(eloc.cpu().numpy(), ref, rtol=2e-5, atol=2e-5 * np.abs(ref).max())
+    seed, t0 = st.rng
+    words, u32 = orng.proposal_stream(seed, t0, CL * N, np.arange(B), np.float32)
+    r = osampler.sample_chain("local", st.σ.cpu().numpy(), W64, b64, a64, chain_length=CL, stream=(words[..., 0], u32.astype(np.float64)))
+    same = np.all(samples.cpu().numpy() == r["samples"], axis=(1, 2))
+    assert same.mean() >= 0.85, same.mean()
