@@ -329,8 +329,8 @@ def main_ours(args):
     other = "float64" if args.dtype == "float32" else "float32"
     extra = None
     if not args.no_second_dtype:
-        k2 = max(2, args.steps // 5) if other == "float64" else args.steps
-        m2 = measure(nk, torch, dist, rank, ws, device, other, k2, 1)
+        k2 = max(3, args.steps // 2) if other == "float64" else args.steps
+        m2 = measure(nk, torch, dist, rank, ws, device, other, k2, 3)
         extra = {"dtype": other, "value": m2["value"], "unit": "samples/s", "steps": k2, "ms_per_step": m2["ms_per_step"],
                  "roofline": m2["roofline"], "mean_energy": m2["stats"].mean}
     cpu = None
