@@ -74,6 +74,7 @@ class MCState:
         self._eloc_cache = {}
         self._eloc_ws = None
         self._forces_ws = None
+        self._sampler_state_previous = None
         self._chain_length = None
         _, ws = world()
         if n_samples is not None and n_samples_per_rank is not None:
@@ -187,6 +188,7 @@ class MCState:
         st = self.sampler_state.replace(n_steps_proc=0, n_accepted_proc=torch.zeros_like(self.sampler_state.n_accepted_proc))
         if sa.reset_chains:
             st = sa.reset(self._model, self._variables, st)
+        self._sampler_state_previous = self.sampler_state  # what the samples are drawn from (serialisation, state.py:555)
         samples, _, eloc, st = sa._launch(self._model, self._variables, st, chain_length, n_discard=n_discard,
                                           operator=operator, path=path)
         self.sampler_state = st
@@ -318,6 +320,18 @@ class MCState:
         if a is not None:
             forces["visible_bias"] = out[N * M + M:]
         return stats, forces
+
+    # ------------------------------------------------------------------ serialisation (state.py:962-1016)
+    def to_state_dict(self):
+        from .serialization import serialize_MCState
+
+        return serialize_MCState(self)
+
+    def from_state_dict(self, state_dict):
+        """Returns a copy of this state restored from ``state_dict`` (the reference's ``flax.serialization.from_state_dict``)."""
+        from .serialization import deserialize_MCState
+
+        return deserialize_MCState(self, state_dict)
 
     def __repr__(self):
         return (f"MCState(\n  hilbert = {self.hilbert},\n  sampler = {self._sampler},\n  n_samples = {self.n_samples},\n"
