@@ -125,6 +125,9 @@ typedef struct nk_sweep_t {
   void *eloc_out;              /* [B, chain_length] */
   int32_t eloc_dtype;          /* NK_F32 | NK_F64 = promote(operator dtype, rbm dtype) */
   int32_t reserved;
+  /* optional: tanh(theta) of every recorded sample, [B, chain_length, M] in the rbm dtype.  The sweep kernels hold it in
+   * registers anyway ((A - B) / (A + B)); nk_forces_rbm takes it instead of recomputing theta for the whole batch */
+  void *tanh_out;
 } nk_sweep_t;
 
 const char *nk_last_error(void);
@@ -189,10 +192,11 @@ int nk_stats_finalize(const double *sums_host, double mean, int64_t n_chains_tot
  *                       over this device's Ns samples; only these sums cross GPUs (all-reduce by the caller);
  *   nk_forces_finalize  out[k] = (dtype) (sums[k] * scale), scale = 1 / n_samples_total (x 2 for the gradient of a
  *                       real-parameter ansatz, netket/vqs/mc/common.py:103-118 `force_to_grad`).
- * workspace: nk_forces_workspace_bytes(rbm, Ns) (theta of the batch + theta-GEMM scratch). */
+ * tanh_theta: [Ns, M] (rbm dtype) as produced by nk_sweep_t.tanh_out, or NULL: theta is then recomputed for the batch
+ * (theta GEMM) into workspace: nk_forces_workspace_bytes(rbm, Ns) bytes (may be NULL when tanh_theta is given). */
 int64_t nk_forces_workspace_bytes(const nk_rbm_t *rbm, int64_t Ns);
 int nk_forces_rbm(void *stream, const nk_rbm_t *rbm, const int8_t *samples, int64_t Ns, const void *eloc, int32_t eloc_dtype,
-                  double mean, double *sums, void *workspace);
+                  double mean, double *sums, void *workspace, const void *tanh_theta);
 int nk_forces_finalize(void *stream, const double *sums, double scale, int64_t n, void *out, int32_t dtype);
 
 /* ---------------------------------------------------------------------------------------------

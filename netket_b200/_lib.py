@@ -54,7 +54,7 @@ class nk_sweep_t(C.Structure):
                 ("machine_pow", C.c_double), ("samples_out", C.c_void_p), ("logp_out", C.c_void_p),
                 ("stream_w0", C.c_void_p), ("stream_u", C.c_void_p), ("clusters", C.c_void_p), ("n_clusters", C.c_int32),
                 ("path", C.c_int32), ("ising", C.POINTER(nk_ising_t)), ("localop", C.POINTER(nk_localop_t)),
-                ("eloc_out", C.c_void_p), ("eloc_dtype", C.c_int32), ("reserved", C.c_int32)]
+                ("eloc_out", C.c_void_p), ("eloc_dtype", C.c_int32), ("reserved", C.c_int32), ("tanh_out", C.c_void_p)]
 
 
 # every symbol include/nkb200.h declares: name -> (restype, argtypes)
@@ -79,7 +79,7 @@ SYMBOLS = {
                                       C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "nk_forces_workspace_bytes": (C.c_int64, [C.POINTER(nk_rbm_t), C.c_int64]),
     "nk_forces_rbm": (C.c_int, [C.c_void_p, C.POINTER(nk_rbm_t), C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_double,
-                                C.c_void_p, C.c_void_p]),
+                                C.c_void_p, C.c_void_p, C.c_void_p]),
     "nk_forces_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_int64, C.c_void_p, C.c_int32]),
     "nk_stats_partial": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_double, C.c_void_p]),
     "nk_stats_finalize": (C.c_int, [C.POINTER(C.c_double), C.c_double, C.c_int64, C.c_int64, C.POINTER(C.c_double)]),

@@ -53,12 +53,12 @@ int random_state(cudaStream_t stream, int8_t *sigma, int64_t B, int32_t N, int32
 int64_t theta_gemm_workspace_bytes(const nk_rbm_t &rbm, int64_t B);
 int theta_gemm(cudaStream_t stream, const nk_rbm_t &rbm, const int8_t *sigma, int64_t B, void *theta_out, void *workspace);
 
-int forces_sums(cudaStream_t stream, const nk_rbm_t &rbm, const int8_t *sigma, const void *theta, const void *eloc, int32_t eloc_dtype,
-                int64_t Ns, double mean, double *sums);
+int forces_sums(cudaStream_t stream, const nk_rbm_t &rbm, const int8_t *sigma, const void *theta, int is_tanh, const void *eloc,
+                int32_t eloc_dtype, int64_t Ns, double mean, double *sums);
 int forces_finalize(cudaStream_t stream, const double *sums, double scale, int64_t n, void *out, int32_t dtype);
 bool forces_tc_supported(const nk_rbm_t &rbm);
-int forces_tc_sums(cudaStream_t stream, const nk_rbm_t &rbm, const int8_t *sigma, const void *theta, const void *eloc, int32_t eloc_dtype,
-                   int64_t Ns, double mean, double *sums);
+int forces_tc_sums(cudaStream_t stream, const nk_rbm_t &rbm, const int8_t *sigma, const void *theta, int is_tanh, const void *eloc,
+                   int32_t eloc_dtype, int64_t Ns, double mean, double *sums);
 
 static int check_rbm(const nk_rbm_t *rbm, const char *who) {
   NK_CHECK_ARG(rbm != nullptr, "%s: rbm is NULL", who);
@@ -186,6 +186,7 @@ int nk_sweep(void *stream, const nk_rbm_t *rbm, nk_chains_t *ch, const nk_sweep_
   if (a->localop) k.localop = *a->localop;
   k.eloc_out = a->eloc_out;
   k.eloc_dtype = a->eloc_dtype;
+  k.tanh_out = a->tanh_out;
 
   // path selection: the tuned fp32 LocalRule kernel (sweep_fast) where it applies, the general product-form kernel
   // (sweep_prod: fp32/fp64, both rules, Ising / LocalOperator) otherwise, the theta-form generic kernel as the last resort
@@ -322,24 +323,28 @@ int64_t nk_forces_workspace_bytes(const nk_rbm_t *rbm, int64_t Ns) {
 }
 
 int nk_forces_rbm(void *stream, const nk_rbm_t *rbm, const int8_t *samples, int64_t Ns, const void *eloc, int32_t eloc_dtype,
-                  double mean, double *sums, void *workspace) {
+                  double mean, double *sums, void *workspace, const void *tanh_theta) {
   int rc = check_rbm(rbm, "nk_forces_rbm");
   if (rc) return rc;
   NK_CHECK_ARG(Ns >= 0 && sums != nullptr, "nk_forces_rbm: bad arguments");
-  NK_CHECK_ARG(Ns == 0 || (samples && eloc && workspace), "nk_forces_rbm: NULL buffer");
+  NK_CHECK_ARG(Ns == 0 || (samples && eloc && (workspace || tanh_theta)), "nk_forces_rbm: NULL buffer");
   NK_CHECK_ARG(eloc_dtype == NK_F32 || eloc_dtype == NK_F64, "nk_forces_rbm: bad eloc_dtype");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n = (size_t)rbm->N * rbm->M + rbm->M + rbm->N;
   NK_CUDA_OK(cudaMemsetAsync(sums, 0, n * sizeof(double), st));
   if (Ns == 0) return NK_OK;
-  void *theta = workspace;
-  void *scratch = reinterpret_cast<char *>(workspace) + ws_theta_bytes(rbm, Ns);
-  rc = theta_gemm(st, *rbm, samples, Ns, theta, scratch);
-  if (rc) return rc;
+  const void *theta = tanh_theta;
+  const int is_tanh = tanh_theta != nullptr ? 1 : 0;
+  if (!is_tanh) {  // recompute theta for the whole batch
+    void *scratch = reinterpret_cast<char *>(workspace) + ws_theta_bytes(rbm, Ns);
+    rc = theta_gemm(st, *rbm, samples, Ns, workspace, scratch);
+    if (rc) return rc;
+    theta = workspace;
+  }
   // fp32: the contraction over the samples runs on the tensor cores (forces_tc.cu); fp64 / large shapes: CUDA cores
   if (forces_tc_supported(*rbm) && getenv("NKB200_FORCES_CUDA_CORE") == nullptr)
-    return forces_tc_sums(st, *rbm, samples, theta, eloc, eloc_dtype, Ns, mean, sums);
-  return forces_sums(st, *rbm, samples, theta, eloc, eloc_dtype, Ns, mean, sums);
+    return forces_tc_sums(st, *rbm, samples, theta, is_tanh, eloc, eloc_dtype, Ns, mean, sums);
+  return forces_sums(st, *rbm, samples, theta, is_tanh, eloc, eloc_dtype, Ns, mean, sums);
 }
 
 int nk_forces_finalize(void *stream, const double *sums, double scale, int64_t n, void *out, int32_t dtype) {

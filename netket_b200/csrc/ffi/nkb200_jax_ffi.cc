@@ -150,7 +150,7 @@ static ffi::Error ForcesImpl(cudaStream_t stream, ffi::AnyBuffer W, ffi::AnyBuff
   nk_rbm_t rbm{W.untyped_data(), b.untyped_data(), a.untyped_data(), (int32_t)d[1], (int32_t)W.dimensions()[1],
                dtype_code(W.element_type()), 0};
   const int rc = nk_forces_rbm(stream, &rbm, samples.typed_data(), d[0], eloc.untyped_data(), dtype_code(eloc.element_type()), mean,
-                               sums->typed_data(), workspace->typed_data());
+                               sums->typed_data(), workspace->typed_data(), /*tanh_theta=*/nullptr);
   return rc == NK_OK ? ffi::Error::Success() : fail();
 }
 

@@ -28,7 +28,8 @@ __device__ __forceinline__ double tanh_t<double>(double x) { return tanh(x); }
 
 struct ForcesArgs {
   const int8_t *sigma;  // [Ns, N]
-  const void *theta;    // [Ns, M] T
+  const void *theta;    // [Ns, M] T: theta, or tanh(theta) if is_tanh
+  int32_t is_tanh;
   const void *eloc;     // [Ns] eloc_dtype
   int32_t eloc_dtype;
   int64_t Ns;
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(F_THREADS) forces_kernel(const __grid_constant
         const int sl = (t >> 6) + 4 * k;
         const int64_t s = s0 + sl;
         T v = T(0);
-        if (j < p.M && s < p.Ns) v = tanh_t<T>(theta[s * p.M + j]) * ws[sl];
+        if (j < p.M && s < p.Ns) v = (p.is_tanh ? theta[s * p.M + j] : tanh_t<T>(theta[s * p.M + j])) * ws[sl];
         xs[sl][t & 63] = v;
         fb += v;
       }
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(F_THREADS) forces_dmma_kernel(const __grid_con
         const int sl = (t >> 6) + 4 * k;
         const int64_t s = s0 + sl;
         double v = 0.0;
-        if (j < p.M && s < p.Ns) v = tanh(theta[s * p.M + j]) * ws[sl];
+        if (j < p.M && s < p.Ns) v = (p.is_tanh ? theta[s * p.M + j] : tanh(theta[s * p.M + j])) * ws[sl];
         xs[sl][t & 63] = v;
         fb += v;
       }
@@ -213,12 +214,13 @@ __global__ void forces_finalize_kernel(const double *__restrict__ sums, double s
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) out[k] = (T)(sums[k] * scale);
 }
 
-int forces_sums(cudaStream_t stream, const nk_rbm_t &rbm, const int8_t *sigma, const void *theta, const void *eloc, int32_t eloc_dtype,
-                int64_t Ns, double mean, double *sums) {
+int forces_sums(cudaStream_t stream, const nk_rbm_t &rbm, const int8_t *sigma, const void *theta, int is_tanh, const void *eloc,
+                int32_t eloc_dtype, int64_t Ns, double mean, double *sums) {
   if (Ns == 0) return NK_OK;
   ForcesArgs a{};
   a.sigma = sigma;
   a.theta = theta;
+  a.is_tanh = is_tanh;
   a.eloc = eloc;
   a.eloc_dtype = eloc_dtype;
   a.Ns = Ns;

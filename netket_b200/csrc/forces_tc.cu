@@ -23,7 +23,8 @@ constexpr int FT_A_BYTES = 16 * FT_SBO;         // 128 rows: 32 KB
 
 struct FtcArgs {
   const int8_t *sigma;
-  const float *theta;
+  const float *theta;  // theta, or tanh(theta) if is_tanh
+  int32_t is_tanh;
   const void *eloc;
   int32_t eloc_dtype;
   int64_t Ns;
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) forces_tc_kernel(const __grid_c
         for (int q = 0; q < 8; ++q) {
           float x = 0.0f;
           if (in_tile)
-            x = tanhf(th[q]) * w[q];
+            x = (p.is_tanh ? th[q] : tanhf(th[q])) * w[q];
           else if (j == p.NT && tile == 0)
             x = w[q];
           const uint32_t h1 = f32_to_bf16_rn(x);
@@ -223,8 +224,8 @@ bool forces_tc_supported(const nk_rbm_t &rbm) {
   return ftc_geometry(rbm, &g);
 }
 
-int forces_tc_sums(cudaStream_t stream, const nk_rbm_t &rbm, const int8_t *sigma, const void *theta, const void *eloc, int32_t eloc_dtype,
-                   int64_t Ns, double mean, double *sums) {
+int forces_tc_sums(cudaStream_t stream, const nk_rbm_t &rbm, const int8_t *sigma, const void *theta, int is_tanh, const void *eloc,
+                   int32_t eloc_dtype, int64_t Ns, double mean, double *sums) {
   if (Ns == 0) return NK_OK;
   FtcGeom g;
   if (!ftc_geometry(rbm, &g)) {
@@ -234,6 +235,7 @@ int forces_tc_sums(cudaStream_t stream, const nk_rbm_t &rbm, const int8_t *sigma
   FtcArgs a{};
   a.sigma = sigma;
   a.theta = reinterpret_cast<const float *>(theta);
+  a.is_tanh = is_tanh;
   a.eloc = eloc;
   a.eloc_dtype = eloc_dtype;
   a.Ns = Ns;

@@ -30,6 +30,7 @@ struct SweepKernelArgs {
   int32_t eloc_dtype;
   int32_t n_pad;  // per-warp sigma stride in smem
   const int *run_if_flag;  // generic kernel only: run iff NULL or *run_if_flag != 0 (fast-path hand-over)
+  void *tanh_out;          // optional [B, chain_length, M]: tanh(theta) of every recorded sample
   int32_t eloc_only;       // sweep_prod only: no proposals, eloc_out[chain] = E_loc(sigma[chain]) (stand-alone local estimator)
 };
 

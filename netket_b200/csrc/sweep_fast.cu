@@ -433,6 +433,16 @@ __global__ void __launch_bounds__(FAST_THREADS, 1)
               const float lp = logpsi_now();
               if (lane == 0) reinterpret_cast<float *>(p.logp_out)[o] = (float)p.machine_pow * lp;
             }
+            if (p.tanh_out != nullptr) {
+              // tanh(theta_j) = (A_j - B_j) / (A_j + B_j): what the forces need, while it is in registers
+              float *to = reinterpret_cast<float *>(p.tanh_out) + o * M;
+#pragma unroll
+              for (int e = 0; e < NE; ++e) {
+                const int j = LM::unit(e, lane);
+                const float av = (e & 1) ? c.A2[e >> 1].y : c.A2[e >> 1].x, bv = (e & 1) ? c.B2[e >> 1].y : c.B2[e >> 1].x;
+                if (j < M) to[j] = __fdividef(av - bv, av + bv);
+              }
+            }
             if (p.eloc_kind == 1) {
               // E_loc = J sum_<ij> s_i s_j - h sum_i exp(delta_i)
               uint32_t sw4[4];

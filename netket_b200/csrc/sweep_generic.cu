@@ -134,6 +134,8 @@ __global__ void __launch_bounds__(256) sweep_generic_kernel(const __grid_constan
             if (p.samples_out != nullptr)
               for (int i = lane; i < N; i += 32) p.samples_out[o * N + i] = sig[i];
             if (p.logp_out != nullptr && lane == 0) reinterpret_cast<T *>(p.logp_out)[o] = pw * logpsi;
+            if (p.tanh_out != nullptr)
+              for (int j = lane; j < M; j += 32) reinterpret_cast<T *>(p.tanh_out)[o * M + j] = tanh(theta[j]);
             if (p.eloc_kind == 1) {
               T e = warp_eloc_ising<T>(r, theta, sig, p.ising.edges, p.ising.n_edges, (T)p.ising.h, (T)p.ising.J, lane);
               if (lane == 0) store_as<T>(p.eloc_out, o, e, p.eloc_dtype);

@@ -802,6 +802,23 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
         const T lp = logpsi_now();
         if (lane == 0 && wk == 0) reinterpret_cast<T *>(s.logp_out)[o] = pw * lp;
       }
+      if (s.tanh_out != nullptr) {
+        // tanh(theta_j) = (A_j - B_j) / (A_j + B_j): what the forces need, while it is in registers
+        T *to = reinterpret_cast<T *>(s.tanh_out) + o * M;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+          const int ju = LM::unit(e, lane), j = wk * MW + ju;
+          T av, bv;
+          if constexpr (F64) {
+            av = A[e];
+            bv = Bv[e];
+          } else {
+            av = (e & 1) ? A[e >> 1].y : A[e >> 1].x;
+            bv = (e & 1) ? Bv[e >> 1].y : Bv[e >> 1].x;
+          }
+          if (ju < MW && j < M) to[j] = (av - bv) / (av + bv);
+        }
+      }
       if (s.eloc_kind != 0) {
         const T e = local_energy();
         if (lane == 0 && wk == 0) store_as<T>(s.eloc_out, o, e, s.eloc_dtype);

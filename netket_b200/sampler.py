@@ -234,8 +234,9 @@ class MetropolisSampler:
         return state.replace(σ=sigma, log_prob=log_prob, n_steps_proc=0, n_accepted_proc=torch.zeros_like(state.n_accepted_proc))
 
     def _launch(self, machine, parameters, state, chain_length, *, n_discard=0, return_log_probabilities=False,
-                operator=None, stream=None, path=_lib.NK_PATH_AUTO, want_samples=True):
-        """One ``nk_sweep`` call.  Returns (samples, logp|None, eloc|None, new_state)."""
+                operator=None, stream=None, path=_lib.NK_PATH_AUTO, want_samples=True, tanh_out=None):
+        """One ``nk_sweep`` call.  Returns (samples, logp|None, eloc|None, new_state).  ``tanh_out``: optional tensor
+        ``(B, chain_length, M)`` that receives tanh(theta) of every recorded sample (input of ``nk_forces_rbm``)."""
         self._check_machine(machine)
         rbm = RBM.c_struct(parameters)
         N = self.hilbert.size
@@ -276,6 +277,10 @@ class MetropolisSampler:
             cl = self.rule.clusters_on(dev)
             a.clusters, a.n_clusters = cl.data_ptr(), int(cl.shape[0])
         a.path = path
+        if tanh_out is not None:
+            if tuple(tanh_out.shape) != (B, chain_length, rbm.M) or tanh_out.dtype != W.dtype or not tanh_out.is_contiguous():
+                raise ValueError("tanh_out must be a contiguous (n_chains, chain_length, n_hidden) tensor of the parameter dtype")
+            a.tanh_out = tanh_out.data_ptr()
         eloc = None
         if operator is not None:
             from .operator import IsingJax, LocalOperatorJax

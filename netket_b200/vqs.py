@@ -75,6 +75,7 @@ class MCState:
         self._eloc_ws = None
         self._forces_ws = None
         self._sampler_state_previous = None
+        self._tanh = None
         self._chain_length = None
         _, ws = world()
         if n_samples is not None and n_samples_per_rank is not None:
@@ -181,16 +182,21 @@ class MCState:
         """Drop the cached samples so that the next access re-samples (state.py:514-519)."""
         self._samples = None
         self._eloc_cache = {}
+        self._tanh = None
 
-    def _run(self, chain_length, n_discard, operator=None, path=_lib.NK_PATH_AUTO):
+    def _run(self, chain_length, n_discard, operator=None, path=_lib.NK_PATH_AUTO, want_tanh=False):
         sa = self._sampler
         # sampler.reset: counters zeroed (and chains re-randomised if reset_chains); log_prob is rebuilt in-kernel
         st = self.sampler_state.replace(n_steps_proc=0, n_accepted_proc=torch.zeros_like(self.sampler_state.n_accepted_proc))
         if sa.reset_chains:
             st = sa.reset(self._model, self._variables, st)
         self._sampler_state_previous = self.sampler_state  # what the samples are drawn from (serialisation, state.py:555)
+        self._tanh = None
+        if want_tanh:  # tanh(theta) of every sample, written by the sweep kernel for the forces (1.7 GB at 2^20 x 400 fp32)
+            W, _, _ = RBM.unpack(self._variables)
+            self._tanh = torch.empty((sa.n_chains_per_rank, chain_length, W.shape[1]), dtype=W.dtype, device=W.device)
         samples, _, eloc, st = sa._launch(self._model, self._variables, st, chain_length, n_discard=n_discard,
-                                          operator=operator, path=path)
+                                          operator=operator, path=path, tanh_out=self._tanh)
         self.sampler_state = st
         return samples, eloc
 
@@ -289,6 +295,10 @@ class MCState:
     def _forces(self, op, factor):
         from .stats import _allreduce
 
+        self._check_operator(op)
+        if self._samples is None:  # one fused launch: sweeps + E_loc + tanh(theta) of every sample
+            self._samples, eloc = self._run(self._chain_length, self._n_discard, operator=op, want_tanh=True)
+            self._eloc_cache = {id(op): eloc}
         eloc = self.local_estimators(op)
         stats = statistics(eloc)
         samples = self.samples
@@ -300,16 +310,19 @@ class MCState:
         e = eloc.reshape(-1).contiguous()
         Ns = s8.shape[0]
         L = _lib.lib()
-        nbytes = int(L.nk_forces_workspace_bytes(C.byref(rbm), Ns))
-        if self._forces_ws is None or self._forces_ws.numel() < nbytes or self._forces_ws.device != dev:
-            self._forces_ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        tanh = self._tanh if (self._tanh is not None and self._tanh.numel() == Ns * M) else None
+        if tanh is None:  # samples were drawn earlier without tanh(theta): recompute theta for the batch
+            nbytes = int(L.nk_forces_workspace_bytes(C.byref(rbm), Ns))
+            if self._forces_ws is None or self._forces_ws.numel() < nbytes or self._forces_ws.device != dev:
+                self._forces_ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
         n = N * M + M + N
         sums = torch.empty(n, dtype=torch.float64, device=dev)
         _, ws = world()
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
             _lib.check(L.nk_forces_rbm(st, C.byref(rbm), _lib.ptr(s8), Ns, _lib.ptr(e), _lib.dtype_code(e.dtype), float(stats.mean),
-                                       _lib.ptr(sums), _lib.ptr(self._forces_ws)))
+                                       _lib.ptr(sums), _lib.ptr(self._forces_ws) if tanh is None else None,
+                                       _lib.ptr(tanh) if tanh is not None else None))
             _allreduce(sums)  # the only cross-device traffic of the gradient: n_parameters doubles
             out = torch.empty(n, dtype=W.dtype, device=dev)
             _lib.check(L.nk_forces_finalize(st, _lib.ptr(sums), factor / float(Ns * ws), n, _lib.ptr(out), _lib.dtype_code(W.dtype)))

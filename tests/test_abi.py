@@ -87,8 +87,9 @@ def test_argument_validation_happens_before_cuda(lib_built):
     assert b"eloc_dtype" in L.nk_last_error()
     assert L.nk_eloc_ising_rbm(None, C.byref(rbm), C.byref(ising), 1, 2, 1, 1, 9, None) == -1
     assert b"bad path" in L.nk_last_error()
-    assert L.nk_forces_rbm(None, C.byref(rbm), 1, 4, 1, 1, 0.0, None, 1) == -1
-    assert L.nk_forces_rbm(None, C.byref(rbm), None, 4, 1, 1, 0.0, 1, 1) == -1
+    assert L.nk_forces_rbm(None, C.byref(rbm), 1, 4, 1, 1, 0.0, None, 1, None) == -1
+    assert L.nk_forces_rbm(None, C.byref(rbm), None, 4, 1, 1, 0.0, 1, 1, None) == -1
+    assert L.nk_forces_rbm(None, C.byref(rbm), 1, 4, 1, 1, 0.0, 1, None, None) == -1  # neither workspace nor tanh(theta)
     assert b"NULL buffer" in L.nk_last_error()
     assert L.nk_forces_finalize(None, None, 1.0, 4, None, 0) == -1
     assert L.nk_forces_workspace_bytes(C.byref(rbm), 1000) >= 1000 * 4 * 4

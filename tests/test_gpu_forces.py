@@ -89,3 +89,30 @@ def test_gradient_descends_the_energy(cuda):
     e1 = vs.expect(op).mean
     assert e1 < e0 - 1.0, (e0, e1)
     assert e1 > -1.2738 * N - 0.5  # exact ground-state energy per site of the critical chain is -4/pi
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_forces_with_and_without_fused_tanh(cuda, dtype):
+    """The sweep kernel writes tanh(theta) of every recorded sample for the forces; when the samples were drawn earlier
+    (`vs.sample()`), theta is recomputed for the batch instead.  Both routes give the oracle's forces."""
+    nk = _nk()
+    g = nk.graph.Hypercube(10, 2)
+    hi = nk.hilbert.Spin(0.5, 100)
+    op = nk.operator.Ising(hi, g, h=3.0)
+    vs = nk.vqs.MCState(nk.sampler.MetropolisLocal(hi, n_chains=64), nk.models.RBM(alpha=4, param_dtype=dtype), n_samples=64 * 4,
+                        n_discard_per_chain=2, seed=5, sampler_seed=6)
+    W, b, a = (t.cpu().numpy().astype(np.float64) for t in nk.models.RBM.unpack(vs.variables))
+    tol = 1e-10 if dtype == np.float64 else 2e-5
+    for fused in (True, False):
+        vs.reset()
+        if not fused:
+            vs.sample()
+            assert vs._tanh is None
+        _, F = vs.expect_and_forces(op)
+        assert (vs._tanh is not None) == fused
+        if fused:  # the kernel's tanh(theta) itself
+            th = np.tanh(orbm.theta(vs.samples.cpu().numpy().reshape(-1, 100), W, b))
+            np.testing.assert_allclose(vs._tanh.cpu().numpy().reshape(-1, 400), th, rtol=0, atol=1e-12 if dtype == np.float64 else 2e-6)
+        ref = oforces.forces(vs.samples.cpu().numpy(), vs.local_estimators(op).cpu().numpy(), W, b, a)
+        for k, got in (("W", F["Dense"]["kernel"]), ("b", F["Dense"]["bias"]), ("a", F["visible_bias"])):
+            np.testing.assert_allclose(got.cpu().numpy(), ref[k], rtol=0, atol=tol * np.abs(ref[k]).max(), err_msg=f"{k} fused={fused}")

@@ -32,7 +32,7 @@ for dtype in (np.float32, np.float64):
     ws = torch.empty(int(L.nk_forces_workspace_bytes(C.byref(rbm), Ns)), dtype=torch.uint8, device=dev)
     sums = torch.empty(N * M + M + N, dtype=torch.float64, device=dev)
     def f():
-        _lib.check(L.nk_forces_rbm(_lib.stream_ptr(dev), C.byref(rbm), _lib.ptr(sig), Ns, _lib.ptr(eloc), 1, 0.0, _lib.ptr(sums), _lib.ptr(ws)))
+        _lib.check(L.nk_forces_rbm(_lib.stream_ptr(dev), C.byref(rbm), _lib.ptr(sig), Ns, _lib.ptr(eloc), 1, 0.0, _lib.ptr(sums), _lib.ptr(ws), None))
     for _ in range(2): f()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
