@@ -20,6 +20,10 @@
 // One warp owns one chain for the whole call; lanes own hidden units; the G table is built once per call by a prep
 // kernel (global memory, padded rows) and staged into shared memory by one TMA bulk copy per CTA.  When the table
 // does not fit (fp64 at N=100, M=400: 325 KB) the first `n_res` rows are resident and the others are read through L2.
+// MULTI instantiations (M > 512, or an fp32 table larger than shared memory): kw warps cooperate on one chain, each
+// owning a slice of the hidden units; per-proposal partial sums are combined through double-buffered shared-memory slots
+// and one named barrier.  N <= 1024 sites (spins as bit words distributed over the lanes), <= 2048 exchange clusters.
+// Optional outputs per recorded sample: sigma, log-probability, local energy, tanh(theta) (for the forces).
 #pragma once
 
 #include <type_traits>
