@@ -159,16 +159,36 @@ __global__ void __launch_bounds__(256) prod_prep_tables(const __grid_constant__ 
   if (tid == 0) {
     const float wmax = __int_as_float(p.flags[2]), rowabs = __int_as_float(p.flags[3]);
     const float LOG2E = 1.4426950408889634f;
-    // renormalisation period r: a lane product has NE_pad factors, each within G^(+-(r+1)) of 1 after r un-normalised
-    // accepts, so NE_pad (r + 1) 4 wmax log2(e) must stay below the exponent range allowed for a lane product
-    const float per = (float)NE_pad * 4.0f * wmax * LOG2E;
-    int renorm = 32;
-    while (renorm >= 1 && (float)(renorm + 1) * per > PROD_EXP_RANGE) renorm >>= 1;
-    if (!(wmax < 1.0e30f)) renorm = 0;
-    // fp64 local energy multiplies M factors of up to two rows: keep 2 x 4 sum_j |W_ij| (+ the visible term) inside the
-    // double range with a wide margin; the per-site exponentials exp(xn +- yn) must be finite as well
+    // Renormalisation period r (A + B = 1 is restored once r accepted moves have piled up, before the next lane product):
+    // a lane product then sees at most r - 1 un-normalised accepts, i.e. factors within G^(+-r) of 1.  Two ranges bind:
+    //   (i)  fp32: a partial lane product (NE_pad / nsplit factors) must stay a normal float:
+    //              (NE_pad / nsplit) r 4 max|W| log2(e) <= PROD_EXP_RANGE;   fp64: NE_pad factors inside the double range;
+    //   (ii) the warp's fixed-point sum must stay inside int32 (2^31 / 2^19 = 4096): r 4 max_i sum_j |W_ij| log2(e) <= 1800.
+    // A LocalOperator may hold same-sign double flips (G_0 G_1 per factor): (i) is then applied with twice the exponent.
+    const float perW = 4.0f * wmax * LOG2E * (s.eloc_kind == 2 ? 2.0f : 1.0f), perRow = 4.0f * rowabs * LOG2E;
+    int renorm = 0, nsplit = 1;
+    if (wmax < 1.0e30f) {
+      auto period = [&](int ns) {
+        const float lim_i = sizeof(T) == 8 ? 900.0f : PROD_EXP_RANGE;
+        float r = 32.0f;
+        if ((float)(NE_pad / ns) * perW > 0.0f) r = fminf(r, lim_i / ((float)(NE_pad / ns) * perW));
+        if (perRow > 0.0f) r = fminf(r, 1800.0f / perRow);
+        return (int)r;
+      };
+      renorm = period(1);
+      if (sizeof(T) == 4 && renorm < 4 && NE_pad >= 4) {  // wide mode: two logarithms per lane product
+        const int r2 = period(2);
+        if (r2 > renorm) {
+          renorm = r2;
+          nsplit = 2;
+        }
+      }
+    }
+    // fp64 local energy multiplies M factors of up to two rows across the warp: keep 2 x 4 sum_j |W_ij| (+ the visible term)
+    // inside the double range with a wide margin; the per-site exponentials exp(xn +- yn) must be finite as well
     if (sizeof(T) == 8 && !(8.0f * rowabs * LOG2E < 900.0f)) renorm = 0;
     if (sizeof(T) == 4 && !(4.0f * rowabs * LOG2E < 2000.0f)) renorm = 0;  // fixed-point constants stay inside int32
+    p.flags[6] = nsplit;
     p.flags[1] = renorm;
     if (renorm < 1 || bad) p.flags[0] = 1;
   }

@@ -62,7 +62,8 @@ struct ProdArgs {
   const unsigned char *gtab;  // [N][row_bytes]
   const unsigned char *aux;   // aux blob (global)
   const void *theta;          // [B][M] T
-  int *flags;                 // [0] hand over to the generic kernel, [1] renormalisation period, [2] max|W| bits, [3] max row sum |W| bits
+  int *flags;                 // [0] hand over to the generic kernel, [1] renormalisation period, [2] max|W| bits, [3] max row sum |W| bits,
+                              // [6] number of logarithms per lane product (1, or 2 = wide mode)
   ProdLayout L;
 };
 
@@ -246,11 +247,19 @@ __device__ __forceinline__ void load_row_p(const unsigned char *row_lane, const 
   if (TAIL == 1) asm volatile("ld.f64 %0, [%1];" : "=d"(g[2 * NFULL]) : "l"(tail_lane));
 }
 
-// prod_q hprod(X_q * g_q + Y_q), two interleaved accumulators
+// A lane product as its two interleaved accumulators (a * b is the product).  Keeping them apart lets the fp32 kernels take
+// two logarithms instead of one when the weights are large ("wide" mode): each partial product then spans half the exponent
+// range, which doubles the largest |W| the product form can handle.
+template <typename T>
+struct LanePair {
+  T a, b;
+};
+// prod_q hprod(X_q * g_q + Y_q)
 template <typename V, int NV>
-__device__ __forceinline__ auto lane_product(const V (&X)[NV], const V (&Y)[NV], const V (&g)[NV]) -> decltype(hprod(X[0])) {
+__device__ __forceinline__ auto lane_product(const V (&X)[NV], const V (&Y)[NV], const V (&g)[NV]) -> LanePair<decltype(hprod(X[0]))> {
+  typedef decltype(hprod(X[0])) T;
   V Pa = vfma(X[0], g[0], Y[0]);
-  if (NV == 1) return hprod(Pa);
+  if (NV == 1) return LanePair<T>{hprod(Pa), T(1)};
   V Pb = vfma(X[NV > 1 ? 1 : 0], g[NV > 1 ? 1 : 0], Y[NV > 1 ? 1 : 0]);
 #pragma unroll
   for (int q = 2; q < NV; ++q) {
@@ -260,13 +269,14 @@ __device__ __forceinline__ auto lane_product(const V (&X)[NV], const V (&Y)[NV],
     else
       Pa = vmul(Pa, c);
   }
-  return hprod(Pa) * hprod(Pb);
+  return LanePair<T>{hprod(Pa), hprod(Pb)};
 }
 // prod_q hprod(c_q)
 template <typename V, int NV>
-__device__ __forceinline__ auto lane_product1(const V (&c)[NV]) -> decltype(hprod(c[0])) {
+__device__ __forceinline__ auto lane_product1(const V (&c)[NV]) -> LanePair<decltype(hprod(c[0]))> {
+  typedef decltype(hprod(c[0])) T;
   V Pa = c[0];
-  if (NV == 1) return hprod(Pa);
+  if (NV == 1) return LanePair<T>{hprod(Pa), T(1)};
   V Pb = c[NV > 1 ? 1 : 0];
 #pragma unroll
   for (int q = 2; q < NV; ++q) {
@@ -275,8 +285,14 @@ __device__ __forceinline__ auto lane_product1(const V (&c)[NV]) -> decltype(hpro
     else
       Pa = vmul(Pa, c[q]);
   }
-  return hprod(Pa) * hprod(Pb);
+  return LanePair<T>{hprod(Pa), hprod(Pb)};
 }
+// fixed-point log2 / log2 / value of a lane product
+__device__ __forceinline__ int lp_fx(const LanePair<float> &p, bool wide) { return wide ? fxlog(p.a) + fxlog(p.b) : fxlog(p.a * p.b); }
+__device__ __forceinline__ int lp_fx(const LanePair<double> &p, bool) { return fxlog(p.a * p.b); }  // a double never leaves its range here
+__device__ __forceinline__ float lp_lg2(const LanePair<float> &p, bool wide) { return wide ? lg2_fast(p.a) + lg2_fast(p.b) : lg2_fast(p.a * p.b); }
+template <typename T>
+__device__ __forceinline__ T lp_val(const LanePair<T> &p) { return p.a * p.b; }
 
 __device__ __forceinline__ uint32_t sel4(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, int i) {
   return (i < 2) ? ((i == 0) ? w0 : w1) : ((i == 2) ? w2 : w3);
@@ -379,6 +395,7 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
   const ProdLayout &L = p.L;
   if (p.flags[0] != 0) return;  // the prep kernels found this configuration outside the product form's range
   const int renorm = p.flags[1];
+  const bool wide = p.flags[6] == 2;  // fp32: two logarithms per lane product (large weights)
   const int N = s.rbm.N, M = s.rbm.M;
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(FULL, tid >> 5, 0);
@@ -556,7 +573,7 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
       V c[NV];
 #pragma unroll
       for (int q = 0; q < NV; ++q) c[q] = vsum2(A[q], Bv[q]);
-      return lane_product1<V, NV>(c);
+      return lp_val(lane_product1<V, NV>(c));
     };
     // log psi of the current state: lncosh(theta_j) = log((A_j + B_j) / (2 sqrt(A_j B_j)))
     auto logpsi_now = [&]() -> T {
@@ -591,7 +608,7 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
     // ------------------------------------------------------------------ fused local energy of the current sample
     // lane product of one candidate (connected configuration) of kind KIND:
     //   0 one site flips, 1 two sites flip to opposite signs (exchange-like), 2 two sites flip to the same sign
-    auto eval_cand = [&](auto kind_c, uint32_t d) -> T {
+    auto eval_cand = [&](auto kind_c, uint32_t d) -> LanePair<T> {
       constexpr int KIND = decltype(kind_c)::value;
       const int s0 = d & CD_SITE_MASK, s1 = (d >> CD_S1_SHIFT) & CD_SITE_MASK;
       const bool p0 = d & CD_POS0;
@@ -662,11 +679,11 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
               mydesc = d;
               mymel = m;
             }
-            const T P = eval_cand(kind_c, d);
+            const LanePair<T> P = eval_cand(kind_c, d);
             if constexpr (F64)
-              v[jj] = P;
+              v[jj] = lp_val(P);
             else
-              v[jj] = lg2_fast(P);
+              v[jj] = lp_lg2(P, wide);
           }
         }
         const T tot = gcomb(bfly<T, NB>(v, lane), [&](T x, T y) { return bf_op(x, y); });
@@ -679,7 +696,9 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
       }
     };
     auto local_energy = [&]() -> T {
-      if (F64) renormalise();  // keeps every product of M factors inside the double range (see prep: row-sum bound)
+      // fp64: A + B = 1 keeps every product of M factors inside the double range (see prep: row-sum bound); fp32: the
+      // candidates' lane products must see at most renorm - 1 un-normalised accepts, like the proposals
+      if (F64 || since >= renorm) renormalise();
       T nrm;                   // fp64: prod_j (A_j + B_j); fp32: its log2
       if constexpr (F64)
         nrm = gcomb(warp_prod(lane_norm()), op_mul);
@@ -716,11 +735,11 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
               if (site < N) {
                 V g[NV];
                 fetch(site, g);
-                const T P = ((bits >> jj) & 1u) ? lane_product<V, NV>(Bv, A, g) : lane_product<V, NV>(A, Bv, g);
+                const LanePair<T> P = ((bits >> jj) & 1u) ? lane_product<V, NV>(Bv, A, g) : lane_product<V, NV>(A, Bv, g);
                 if constexpr (F64)
-                  v[jj] = P;
+                  v[jj] = lp_val(P);
                 else
-                  v[jj] = lg2_fast(P);
+                  v[jj] = lp_lg2(P, wide);
               }
             }
             const T tot = gcomb(bfly<T, NB>(v, lane), [&](T x, T y) { return bf_op(x, y); });
@@ -872,8 +891,8 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
             const Rc &rc = rctab[site];
             const int fx = rc.fx, fy = rc.fy;
             const bool pos = sbit(site) != 0;  // sigma = -1 -> +1
-            const T P = pos ? lane_product<V, NV>(Bv, A, g) : lane_product<V, NV>(A, Bv, g);
-            const int Rp = gcomb(__reduce_add_sync(FULL, fxlog(P)), op_add);
+            const LanePair<T> P = pos ? lane_product<V, NV>(Bv, A, g) : lane_product<V, NV>(A, Bv, g);
+            const int Rp = gcomb(__reduce_add_sync(FULL, lp_fx(P, wide)), op_add);
             const int X = (int)((uint32_t)Rp - (uint32_t)R + (uint32_t)(pos ? fx + fy : fx - fy));
             bool acc;
             if constexpr (F64) {
@@ -882,7 +901,7 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
               else if (thr >= X + PROD_FX_BAND)
                 acc = false;
               else
-                acc = exact_decide(gcomb(exact_logratio(P, lane_norm()), op_add), pos ? rc.xn + rc.yn : rc.xn - rc.yn,
+                acc = exact_decide(gcomb(exact_logratio(lp_val(P), lane_norm()), op_add), pos ? rc.xn + rc.yn : rc.xn - rc.yn,
                                    __shfl_sync(FULL, u_l, k), pw, 0.0);
             } else {
               acc = thr < X;
@@ -955,8 +974,8 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
               V c[NV];
 #pragma unroll
               for (int q = 0; q < NV; ++q) c[q] = vfma(Bv[q], g[q], t[q]);
-              const T P = lane_product1<V, NV>(c);
-              const int Rp = __reduce_add_sync(FULL, fxlog(P));
+              const LanePair<T> P = lane_product1<V, NV>(c);
+              const int Rp = __reduce_add_sync(FULL, lp_fx(P, wide));
               const int X = (int)((uint32_t)Rp - (uint32_t)R + (uint32_t)cfix);
               bool acc;
               if constexpr (F64) {
@@ -965,7 +984,7 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
                 else if (thr >= X + PROD_FX_BAND)
                   acc = false;
                 else
-                  acc = exact_decide(exact_logratio(P, lane_norm()), rp.xn + rp.yn + rm.xn - rm.yn, __shfl_sync(FULL, u_l, k), pw,
+                  acc = exact_decide(exact_logratio(lp_val(P), lane_norm()), rp.xn + rp.yn + rm.xn - rm.yn, __shfl_sync(FULL, u_l, k), pw,
                                      log((double)n_hop) - log((double)nhp));
               } else {
                 acc = thr < X;

@@ -611,3 +611,39 @@ def test_auto_path_boundaries_fp32(cuda, N, M):
     r = osampler.sample_chain("local", st.σ.cpu().numpy(), W64, b64, a64, chain_length=CL, stream=(words[..., 0], u32.astype(np.float64)))
     same = np.all(samples.cpu().numpy() == r["samples"], axis=(1, 2))
     assert same.mean() >= 0.85, same.mean()
+
+
+# ----------------------------------------------------------------------------------------- large weights (trained networks)
+def _prod_flags(sa, B, M, esz):
+    """The hand-over / range flags the prep kernels left in the sampler's workspace (netket_b200/csrc/api.cu layout)."""
+    ws = next(iter(sa.__dict__["_ws_cache"].values()))
+    off = (B * M * esz + 255) & ~255
+    return ws[off:off + 32].view(torch.int32).cpu().numpy()
+
+
+@pytest.mark.parametrize("dtype,std,expect_split", [(np.float32, 0.2, 2), (np.float32, 0.35, 2), (np.float32, 0.05, 1), (np.float64, 0.2, 1)])
+def test_prod_wide_range_weights(cuda, dtype, std, expect_split):
+    """max|W| up to ~1.5 at N=100, M=400 stays on the product-form kernel (fp32: two logarithms per lane product and a
+    short renormalisation period) instead of handing over to the theta-form kernel; chains and E_loc still match the oracle."""
+    nk = _nk()
+    B, CL = 48, 3
+    g, hi, (W, b, a), var, model, sa, _, e, col = _case(nk, "local", 10, 2, 4, dtype, std, B)
+    op = nk.operator.Ising(hi, g, h=3.0)
+    st = sa.init_state(model, var, seed=13)
+    samples, _, eloc, st2 = sa._launch(model, var, st, CL, n_discard=1, operator=op, path=PROD)
+    flags = _prod_flags(sa, B, 400, np.dtype(dtype).itemsize)
+    assert flags[0] == 0, "the product-form kernel handed over to the theta-form kernel"
+    assert flags[1] >= 1 and flags[6] == expect_split, flags[:8]
+    W64, b64, a64 = _f64(W, b, a)
+    ref = oest.local_estimators(samples.cpu().numpy(), lambda x: oops.ising_conn_padded(x, e, 3.0, 1.0), W64, b64, a64)
+    tol = 1e-10 if dtype == np.float64 else 3e-5
+    np.testing.assert_allclose(eloc.cpu().numpy(), ref, rtol=tol, atol=tol * np.abs(ref).max())
+    seed, t0 = st.rng
+    if dtype == np.float64:
+        r = osampler.sample_chain("local", st.σ.cpu().numpy(), W64, b64, a64, chain_length=CL + 1, seed=seed, t0=t0)
+        assert np.array_equal(samples.cpu().numpy(), r["samples"][:, 1:])
+    else:
+        words, u32 = orng.proposal_stream(seed, t0, (CL + 1) * 100, np.arange(B), np.float32)
+        r = osampler.sample_chain("local", st.σ.cpu().numpy(), W64, b64, a64, chain_length=CL + 1, stream=(words[..., 0], u32.astype(np.float64)))
+        same = np.all(samples.cpu().numpy() == r["samples"][:, 1:], axis=(1, 2))
+        assert same.mean() >= 0.85, same.mean()
