@@ -210,12 +210,23 @@ int nk_sweep(void *stream, const nk_rbm_t *rbm, nk_chains_t *ch, const nk_sweep_
     NK_CUDA_OK(cudaMemsetAsync(flags, 0, 256, st));
     rc = theta_gemm(st, *rbm, ch->sigma, ch->B, theta, scratch);  // theta = sigma W + b  (the only dense contraction)
     if (rc) return rc;
-    rc = fast_ok ? sweep_fast(st, k, reinterpret_cast<const float *>(theta), flags) : sweep_prod(st, k, theta, flags, tables);
+    const int *guard = flags;  // the flag the theta-form kernel waits on
+    if (fast_ok) {
+      // tuned fp32 kernel first; if the weights are beyond its range (flags[0]) the general kernel's wide mode takes over
+      // in-stream, and only if that gives up as well (flags[5]) the theta-form kernel runs
+      rc = sweep_fast(st, k, reinterpret_cast<const float *>(theta), flags);
+      if (rc == NK_OK && a->path != NK_PATH_FAST && sweep_prod_supported(k)) {
+        rc = sweep_prod(st, k, theta, flags, tables, flags, 5);
+        guard = flags + 5;
+      }
+    } else {
+      rc = sweep_prod(st, k, theta, flags, tables);
+    }
     if (rc == NK_OK) {
       // weights beyond the product form's range (a property of the data, found by the prep kernels): the product kernel
       // raises flags[0] and exits; this one then runs.  Also enqueued when the path was forced, so that a forced path can
       // never return without having produced its outputs.
-      k.run_if_flag = flags;
+      k.run_if_flag = guard;
       rc = sweep_generic(st, k);
     }
   } else {

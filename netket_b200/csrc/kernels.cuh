@@ -42,6 +42,8 @@ int sweep_fast(cudaStream_t stream, const SweepKernelArgs &a, const float *theta
 // sweep_prod.cu — general product-form path (fp32 / fp64, LocalRule / ExchangeRule, Ising / LocalOperator E_loc)
 bool sweep_prod_supported(const SweepKernelArgs &a);
 size_t sweep_prod_workspace_bytes(const nk_rbm_t &rbm);
-int sweep_prod(cudaStream_t stream, const SweepKernelArgs &a, const void *theta_ws, int *flags, void *tables_ws);
+// run_if: launch guard (NULL: always run); flags[giveup] is raised when the weights are outside the product form's range
+int sweep_prod(cudaStream_t stream, const SweepKernelArgs &a, const void *theta_ws, int *flags, void *tables_ws, const int *run_if = nullptr,
+               int giveup = 0);
 
 }  // namespace nk

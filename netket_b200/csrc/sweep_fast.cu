@@ -18,8 +18,9 @@
 // W is brought in once per CTA by TMA bulk copies and turned into the G table in place.
 // The binding resource is the shared-memory read of one G row (M floats) per proposal per chain.
 //
-// Validity: 8 * (4 max|W| log2 e) * 2 <= 120 (|W| <~ 1.3); otherwise the kernel raises a device flag and the
-// theta-form generic kernel, always enqueued behind it, does the work (no host round trip).
+// Validity: 2 NP * (4 max|W| log2 e) <= 120 (|W| <~ 1.5 at 14 units per lane); otherwise the kernel raises a device flag and
+// the kernels enqueued behind it do the work without a host round trip: the general product-form kernel in its wide mode
+// (two logarithms per lane product, |W| <~ 3), then the theta-form kernel.
 #include "kernels.cuh"
 
 namespace nk {
@@ -249,14 +250,14 @@ __global__ void __launch_bounds__(FAST_THREADS, 1)
   __syncthreads();
   wmax = 0.0f;
   for (int w = 0; w < FAST_WARPS; ++w) wmax = fmaxf(wmax, red[w]);
-  // renormalisation period r: a lane product has 2*NP factors, each within G^(+-(r+1)) of 1 after r un-normalised
-  // accepts, so 2 NP (r + 1) 4 wmax log2(e) must stay below the fp32 exponent range (and 32 lanes of it, times
-  // FX_SCALE, inside int32)
+  // renormalisation period r: A + B = 1 is restored once r accepted moves have piled up, before the next lane product, so
+  // a product (2*NP factors) sees at most r - 1 un-normalised accepts: factors within G^(+-r) of 1.  2 NP r 4 wmax log2(e)
+  // must stay below the fp32 exponent range (and 32 lanes of it, times FX_SCALE, inside int32)
   int renorm = 0;
   {
     const float per = (float)(2 * NP) * 4.0f * wmax * LOG2E;
     renorm = 32;
-    while (renorm >= 1 && (float)(renorm + 1) * per > EXP_RANGE) renorm >>= 1;
+    while (renorm >= 1 && (float)renorm * per > EXP_RANGE) renorm >>= 1;
     if (!(wmax < 1.0e30f)) renorm = 0;  // NaN / Inf weights
   }
   if (renorm < 1) {  // weights too large for the product form: hand over to the generic kernel queued behind us
@@ -445,6 +446,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1)
             }
             if (p.eloc_kind == 1) {
               // E_loc = J sum_<ij> s_i s_j - h sum_i exp(delta_i)
+              if (c.since >= renorm) renormalise();  // the flips below must see at most r - 1 un-normalised accepts too
               uint32_t sw4[4];
 #pragma unroll
               for (int b = 0; b < 4; ++b) sw4[b] = __ballot_sync(0xffffffffu, (c.mybits >> b) & 1u);

@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(128) prod_prep_rows(const __grid_constant__ Pr
   // row layout: kw segments (one per cooperating warp) of MP elements; segment k holds hidden units [k mw, (k+1) mw)
   typedef typename VecOf<T>::Rc Rc;
   __shared__ double red[3][4];
+  if (p.run_if != nullptr && *p.run_if == 0) return;
   const int i = blockIdx.x, N = p.s.rbm.N, M = p.s.rbm.M;
   (void)N;
   const T *W = reinterpret_cast<const T *>(p.s.rbm.W) + (size_t)i * M;
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(256) prod_prep_tables(const __grid_constant__ 
   const ProdLayout &L = p.L;
   unsigned char *aux = const_cast<unsigned char *>(p.aux);
   const int N = s.rbm.N, tid = threadIdx.x, nt = blockDim.x;
+  if (p.run_if != nullptr && *p.run_if == 0) return;
   if (tid == 0) bad = 0;
   for (int i = tid; i < 1024; i += nt) deg[i] = 0;
   __syncthreads();
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(256) prod_prep_tables(const __grid_constant__ 
     if (sizeof(T) == 4 && !(4.0f * rowabs * LOG2E < 2000.0f)) renorm = 0;  // fixed-point constants stay inside int32
     p.flags[6] = nsplit;
     p.flags[1] = renorm;
-    if (renorm < 1 || bad) p.flags[0] = 1;
+    if (renorm < 1 || bad) p.flags[p.giveup] = 1;
   }
 }
 
@@ -357,7 +359,8 @@ size_t sweep_prod_workspace_bytes(const nk_rbm_t &rbm) {
   return (((size_t)rbm.N * ps.kw * ps.seg_bytes + 255) & ~(size_t)255) + PROD_AUX_MAX;
 }
 
-int sweep_prod(cudaStream_t stream, const SweepKernelArgs &a, const void *theta_ws, int *flags, void *tables_ws) {
+int sweep_prod(cudaStream_t stream, const SweepKernelArgs &a, const void *theta_ws, int *flags, void *tables_ws, const int *run_if,
+               int giveup) {
   ProdShape ps;
   ProdArgs pa{};
   if (!prod_shape(a.rbm.M, a.rbm.dtype, a.rule, &ps) || !prod_layout(a, ps, &pa.L)) {
@@ -369,6 +372,8 @@ int sweep_prod(cudaStream_t stream, const SweepKernelArgs &a, const void *theta_
   pa.aux = pa.gtab + (((size_t)a.rbm.N * pa.L.row_bytes + 255) & ~(size_t)255);
   pa.theta = theta_ws;
   pa.flags = flags;
+  pa.run_if = run_if;
+  pa.giveup = giveup;
   const bool multi = pa.L.multi != 0;
   if (a.rbm.dtype == NK_F32) {
     prod_prep_rows<float><<<a.rbm.N, 128, 0, stream>>>(pa, ps.mp);

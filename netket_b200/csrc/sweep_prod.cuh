@@ -65,6 +65,10 @@ struct ProdArgs {
   int *flags;                 // [0] hand over to the generic kernel, [1] renormalisation period, [2] max|W| bits, [3] max row sum |W| bits,
                               // [6] number of logarithms per lane product (1, or 2 = wide mode)
   ProdLayout L;
+  // chaining behind the tuned fp32 kernel: run only if *run_if != 0 (NULL: always); flags[giveup] = 1 tells the theta-form
+  // kernel queued behind to take over
+  const int *run_if;
+  int giveup;
 };
 
 struct RcF {  // per-site constants, fp32 kernels (log2 units)
@@ -393,7 +397,8 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
   extern __shared__ __align__(128) unsigned char smem[];
   const SweepKernelArgs &s = p.s;
   const ProdLayout &L = p.L;
-  if (p.flags[0] != 0) return;  // the prep kernels found this configuration outside the product form's range
+  if (p.run_if != nullptr && *p.run_if == 0) return;  // the kernel in front of this one did the work
+  if (p.flags[p.giveup] != 0) return;  // the prep kernels found this configuration outside the product form's range
   const int renorm = p.flags[1];
   const bool wide = p.flags[6] == 2;  // fp32: two logarithms per lane product (large weights)
   const int N = s.rbm.N, M = s.rbm.M;

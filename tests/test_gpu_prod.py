@@ -647,3 +647,26 @@ def test_prod_wide_range_weights(cuda, dtype, std, expect_split):
         r = osampler.sample_chain("local", st.σ.cpu().numpy(), W64, b64, a64, chain_length=CL + 1, stream=(words[..., 0], u32.astype(np.float64)))
         same = np.all(samples.cpu().numpy() == r["samples"][:, 1:], axis=(1, 2))
         assert same.mean() >= 0.85, same.mean()
+
+
+@pytest.mark.parametrize("std,fast_gives_up,prod_gives_up", [(0.05, 0, 0), (0.2, 0, 0), (0.35, 0, 0), (0.5, 1, 0), (0.9, 1, 1)])
+def test_fp32_auto_chain_large_weights(cuda, std, fast_gives_up, prod_gives_up):
+    """NK_PATH_AUTO, fp32 TFIM: tuned kernel -> (weights beyond its range) general kernel in wide mode -> (beyond that) theta-form
+    kernel, all enqueued in-stream; whichever kernel does the work, E_loc and the chains match the oracle."""
+    nk = _nk()
+    B, CL = 48, 2
+    g, hi, (W, b, a), var, model, sa, _, e, col = _case(nk, "local", 10, 2, 4, np.float32, std, B)
+    op = nk.operator.Ising(hi, g, h=3.0)
+    st = sa.init_state(model, var, seed=13)
+    samples, _, eloc, st2 = sa._launch(model, var, st, CL, n_discard=1, operator=op, path=0)
+    flags = _prod_flags(sa, B, 400, 4)
+    assert (int(flags[0] != 0), int(flags[5] != 0)) == (fast_gives_up, prod_gives_up), flags[:8]
+    W64, b64, a64 = _f64(W, b, a)
+    ref = oest.local_estimators(samples.cpu().numpy(), lambda x: oops.ising_conn_padded(x, e, 3.0, 1.0), W64, b64, a64)
+    np.testing.assert_allclose(eloc.cpu().numpy(), ref, rtol=3e-5, atol=3e-5 * np.abs(ref).max())
+    seed, t0 = st.rng
+    words, u32 = orng.proposal_stream(seed, t0, (CL + 1) * 100, np.arange(B), np.float32)
+    r = osampler.sample_chain("local", st.σ.cpu().numpy(), W64, b64, a64, chain_length=CL + 1, stream=(words[..., 0], u32.astype(np.float64)))
+    same = np.all(samples.cpu().numpy() == r["samples"][:, 1:], axis=(1, 2))
+    assert same.mean() >= 0.85, same.mean()
+    assert set(np.unique(samples.cpu().numpy())) <= {-1, 1}
