@@ -188,7 +188,8 @@ __global__ void __launch_bounds__(256) prod_prep_tables(const __grid_constant__ 
     }
     // fp64 local energy multiplies M factors of up to two rows across the warp: keep 2 x 4 sum_j |W_ij| (+ the visible term)
     // inside the double range with a wide margin; the per-site exponentials exp(xn +- yn) must be finite as well
-    if (sizeof(T) == 8 && !(8.0f * rowabs * LOG2E < 900.0f)) renorm = 0;
+    // (beyond that the fp64 local energy reduces (mantissa, exponent) pairs and works in the log2 domain: flags[7])
+    p.flags[7] = (sizeof(T) == 8 && !(8.0f * rowabs * LOG2E < 900.0f)) ? 1 : 0;
     if (sizeof(T) == 4 && !(4.0f * rowabs * LOG2E < 2000.0f)) renorm = 0;  // fixed-point constants stay inside int32
     p.flags[6] = nsplit;
     p.flags[1] = renorm;

@@ -63,7 +63,7 @@ struct ProdArgs {
   const unsigned char *aux;   // aux blob (global)
   const void *theta;          // [B][M] T
   int *flags;                 // [0] hand over to the generic kernel, [1] renormalisation period, [2] max|W| bits, [3] max row sum |W| bits,
-                              // [6] number of logarithms per lane product (1, or 2 = wide mode)
+                              // [6] number of logarithms per lane product (1, or 2 = wide mode), [7] fp64 E_loc in (mantissa, exponent) form
   ProdLayout L;
   // chaining behind the tuned fp32 kernel: run only if *run_if != 0 (NULL: always); flags[giveup] = 1 tells the theta-form
   // kernel queued behind to take over
@@ -336,6 +336,7 @@ static __device__ __noinline__ bool exact_decide(double d, double cst, double u,
 // (l >> 1) & (NB - 1).  fp32: additive (log2 partials); fp64: multiplicative (the lane products themselves).
 __device__ __forceinline__ float bf_op(float a, float b) { return a + b; }
 __device__ __forceinline__ double bf_op(double a, double b) { return a * b; }
+__device__ __forceinline__ int bf_op(int a, int b) { return a + b; }  // exponents of split doubles
 template <typename T, int NB>
 __device__ __forceinline__ T bfly(T (&v)[NB], int lane) {
 #pragma unroll
@@ -401,6 +402,7 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
   if (p.flags[p.giveup] != 0) return;  // the prep kernels found this configuration outside the product form's range
   const int renorm = p.flags[1];
   const bool wide = p.flags[6] == 2;  // fp32: two logarithms per lane product (large weights)
+  const bool wide_e = F64 && p.flags[7] != 0;  // fp64 local energy: products across the warp as (mantissa, exponent) pairs
   const int N = s.rbm.N, M = s.rbm.M;
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(FULL, tid >> 5, 0);
@@ -662,6 +664,40 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
     // NB candidates at a time: NB independent lane products, then one transposed butterfly.
     constexpr int NB = F64 ? 8 : 16;  // candidates per butterfly (register budget)
     const int myidx = (lane >> 1) & (NB - 1);
+    // fp64: warp (and chain) total of candidate (lane >> 1) & (NB - 1).  Narrow mode: the plain product.  Wide mode (row sums
+    // of |W| so large that a product of M factors could leave the double range): every lane product is split into mantissa
+    // and exponent, mantissas are multiplied (32 x [1, 2) stays tiny), exponents are added in a second butterfly.
+    auto reduce_cands = [&](T(&v)[NB], int &tot_e) -> T {
+      tot_e = 0;
+      if constexpr (F64) {
+        if (wide_e) {
+          int ve[NB];
+#pragma unroll
+          for (int jj = 0; jj < NB; ++jj) {
+            const int hi = __double2hiint(v[jj]), lo = __double2loint(v[jj]);
+            ve[jj] = ((hi >> 20) & 0x7ff) - 1023;
+            v[jj] = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, lo);
+          }
+          tot_e = gcomb(bfly<int, NB>(ve, lane), op_add);
+        }
+      }
+      return gcomb(bfly<T, NB>(v, lane), [&](T x, T y) { return bf_op(x, y); });
+    };
+    // psi(sigma') / psi(sigma) of one candidate from its total (fp32: log2 domain; fp64: product, or log2 domain in wide mode)
+    auto cand_ratio = [&](T tot, int tot_e, T nrm, uint32_t d) -> T {
+      if constexpr (F64) {
+        if (wide_e) {
+          const int s0 = d & CD_SITE_MASK, s1 = (d >> CD_S1_SHIFT) & CD_SITE_MASK;
+          double c = 0.0;  // natural-log constant: sum over the changed sites of 2 sum_j W_ij +- 2 a_i
+          if (d & CD_CHG0) c += (d & CD_POS0) ? rctab[s0].xn + rctab[s0].yn : rctab[s0].xn - rctab[s0].yn;
+          if (d & CD_CHG1) c += (d & CD_POS1) ? rctab[s1].xn + rctab[s1].yn : rctab[s1].xn - rctab[s1].yn;
+          return exp2(log2(tot) - log2(nrm) + (double)tot_e + 1.4426950408889634 * c);
+        }
+        return tot * cand_const(d) / nrm;
+      } else {
+        return ex2_fast(tot - nrm + cand_const(d));
+      }
+    };
     auto eval_round = [&](auto kind_c, uint32_t desc, T mel, T nrm, T &off_l) {
       constexpr int KIND = decltype(kind_c)::value;
       const bool both = (desc & CD_CHG0) && (desc & CD_CHG1);
@@ -691,13 +727,9 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
               v[jj] = lp_lg2(P, wide);
           }
         }
-        const T tot = gcomb(bfly<T, NB>(v, lane), [&](T x, T y) { return bf_op(x, y); });
-        if ((lane & 1) == 0 && lane < 2 * NB && (mydesc & CD_VALID)) {
-          if constexpr (F64)
-            off_l += mymel * (tot * cand_const(mydesc) / nrm);
-          else
-            off_l += mymel * ex2_fast(tot - nrm + cand_const(mydesc));
-        }
+        int tot_e;
+        const T tot = reduce_cands(v, tot_e);
+        if ((lane & 1) == 0 && lane < 2 * NB && (mydesc & CD_VALID)) off_l += mymel * cand_ratio(tot, tot_e, nrm, mydesc);
       }
     };
     auto local_energy = [&]() -> T {
@@ -747,14 +779,12 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
                   v[jj] = lp_lg2(P, wide);
               }
             }
-            const T tot = gcomb(bfly<T, NB>(v, lane), [&](T x, T y) { return bf_op(x, y); });
+            int tot_e;
+            const T tot = reduce_cands(v, tot_e);
             const int mys = base + myidx;
             if ((lane & 1) == 0 && lane < 2 * NB && mys < N) {
-              const bool pos = (bits >> myidx) & 1u;
-              if constexpr (F64)
-                off_l += mel * (tot * (pos ? rctab[mys].ep : rctab[mys].em) / nrm);
-              else
-                off_l += mel * ex2_fast(tot - nrm + (pos ? rctab[mys].x2 + rctab[mys].y2 : rctab[mys].x2 - rctab[mys].y2));
+              const uint32_t dd = CD_CHG0 | (uint32_t)mys | (((bits >> myidx) & 1u) ? CD_POS0 : 0u);
+              off_l += mel * cand_ratio(tot, tot_e, nrm, dd);
             }
           }
         }

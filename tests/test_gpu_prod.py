@@ -621,10 +621,13 @@ def _prod_flags(sa, B, M, esz):
     return ws[off:off + 32].view(torch.int32).cpu().numpy()
 
 
-@pytest.mark.parametrize("dtype,std,expect_split", [(np.float32, 0.2, 2), (np.float32, 0.35, 2), (np.float32, 0.05, 1), (np.float64, 0.2, 1)])
-def test_prod_wide_range_weights(cuda, dtype, std, expect_split):
+@pytest.mark.parametrize("dtype,std,expect_split,expect_wide_e", [(np.float32, 0.2, 2, 0), (np.float32, 0.35, 2, 0), (np.float32, 0.05, 1, 0),
+                                                                   (np.float64, 0.2, 1, 0), (np.float64, 0.35, 1, 1), (np.float64, 0.5, 1, 1)])
+def test_prod_wide_range_weights(cuda, dtype, std, expect_split, expect_wide_e):
     """max|W| up to ~1.5 at N=100, M=400 stays on the product-form kernel (fp32: two logarithms per lane product and a
-    short renormalisation period) instead of handing over to the theta-form kernel; chains and E_loc still match the oracle."""
+    short renormalisation period; fp64: local energy reduced as (mantissa, exponent) pairs once the row sums of |W| could take a
+    product of M factors out of the double range) instead of handing over to the theta-form kernel; chains and E_loc still
+    match the oracle."""
     nk = _nk()
     B, CL = 48, 3
     g, hi, (W, b, a), var, model, sa, _, e, col = _case(nk, "local", 10, 2, 4, dtype, std, B)
@@ -633,7 +636,7 @@ def test_prod_wide_range_weights(cuda, dtype, std, expect_split):
     samples, _, eloc, st2 = sa._launch(model, var, st, CL, n_discard=1, operator=op, path=PROD)
     flags = _prod_flags(sa, B, 400, np.dtype(dtype).itemsize)
     assert flags[0] == 0, "the product-form kernel handed over to the theta-form kernel"
-    assert flags[1] >= 1 and flags[6] == expect_split, flags[:8]
+    assert flags[1] >= 1 and flags[6] == expect_split and flags[7] == expect_wide_e, flags[:8]
     W64, b64, a64 = _f64(W, b, a)
     ref = oest.local_estimators(samples.cpu().numpy(), lambda x: oops.ising_conn_padded(x, e, 3.0, 1.0), W64, b64, a64)
     tol = 1e-10 if dtype == np.float64 else 3e-5
