@@ -185,6 +185,38 @@ int nk_stats_partial(void *stream, const void *data, int32_t dtype, int64_t n_ch
 /* host-only arithmetic: sums_host = all-reduced phase-1 partials; out_host = {mean, error_of_mean, variance, tau_corr, R_hat} */
 int nk_stats_finalize(const double *sums_host, double mean, int64_t n_chains_total, int64_t L, double *out_host);
 
+/* Streaming statistics: OnlineStats (netket/_src/stats/online_stats/accumulator.py:31-447), the accumulator behind
+ * thermalise_mcmc / check_mc_convergence / expect_to_precision (netket/_src/vqs/check_mc_convergence.py,
+ * expect_to_precision.py).  The state is the reference's pytree, field for field, as device arrays of doubles:
+ *   chain_count, chain_mean, chain_M2          [n_chains]
+ *   cross_sum, m1_sum, m2_sum, pair_count      [n_chains, max_lag + 1]   (absent when max_lag == 0)
+ *   chain_buf                                  [n_chains, max_lag]       last samples of each chain, right-aligned
+ * buf_len = number of valid samples in chain_buf; the caller advances it: min(buf_len + n, max_lag).
+ *   nk_online_stats_update    `_update_arrays` (kernels.py:116-190): merges data [n_chains, n] (dtype) into `in`, writing
+ *                             `out` (may be the same struct: in-place).  decay: 1.0 for the reference's None.
+ *   nk_online_stats_summary   sums over this device's chains; phase 0 -> 3 doubles {sum count, sum count*mean, sum mean};
+ *                             phase 1 (given gmean = [1]/[0] and mbar = [2]/n_chains of the all-reduced phase 0)
+ *                             -> NK_ONLINE_NSUM + max_lag + 1 doubles.  Only these sums cross GPUs.
+ *   nk_online_stats_finalize  host arithmetic on the all-reduced sums: out_host[NK_ONLINE_NOUT] = {mean, error_of_mean,
+ *                             variance, tau_corr, R_hat, tau_corr_batch, tau_corr_acf (Geyer IPS + IMS), acf window
+ *                             saturated (0/1), tau_corr reliable (0/1)}; acf_host [max_lag + 1] or NULL (NaN = no acf). */
+typedef struct {
+  double *chain_count, *chain_mean, *chain_M2;
+  double *cross_sum, *m1_sum, *m2_sum, *pair_count;
+  double *chain_buf;
+  int64_t n_chains;
+  int32_t max_lag;
+  int32_t buf_len;
+} nk_online_stats_t;
+#define NK_ONLINE_NSUM 4
+#define NK_ONLINE_NOUT 9
+#define NK_ONLINE_MAX_LAG 4096
+int nk_online_stats_update(void *stream, const nk_online_stats_t *in, const nk_online_stats_t *out, const void *data, int32_t dtype,
+                           int64_t n, double decay);
+int nk_online_stats_summary(void *stream, const nk_online_stats_t *state, int32_t phase, double gmean, double mbar, double *sums_out);
+int nk_online_stats_finalize(const double *phase0_host, const double *phase1_host, int64_t n_chains_total, int64_t n_samples_total,
+                             int32_t max_lag, double *out_host, double *acf_host);
+
 /* Forces F_k = < d log psi / d p_k * (E_loc - mean) > of the RBM over a batch of samples: the vjp of
  * netket/vqs/mc/mc_state/expect_forces.py:69-112 (`forces_expect_hermitian`) in closed form
  * (d/dW_ij = sigma_i tanh theta_j, d/db_j = tanh theta_j, d/da_i = sigma_i).

@@ -18,6 +18,7 @@ NK_F32, NK_F64 = 0, 1
 NK_RULE_LOCAL, NK_RULE_EXCHANGE = 0, 1
 NK_PATH_AUTO, NK_PATH_GENERIC, NK_PATH_FAST, NK_PATH_PROD = 0, 1, 2, 3
 NK_STATS_NPARTIAL = 8
+NK_ONLINE_NSUM, NK_ONLINE_NOUT, NK_ONLINE_MAX_LAG = 4, 9, 4096
 
 
 class NkError(RuntimeError):
@@ -47,6 +48,12 @@ class nk_localop_t(C.Structure):
 class nk_chains_t(C.Structure):
     _fields_ = [("sigma", C.c_void_p), ("log_prob", C.c_void_p), ("n_accepted", C.c_void_p), ("workspace", C.c_void_p),
                 ("B", C.c_int64), ("seed", C.c_uint64), ("t", C.c_uint64), ("chain_offset", C.c_uint64)]
+
+
+class nk_online_stats_t(C.Structure):
+    _fields_ = [("chain_count", C.c_void_p), ("chain_mean", C.c_void_p), ("chain_M2", C.c_void_p), ("cross_sum", C.c_void_p),
+                ("m1_sum", C.c_void_p), ("m2_sum", C.c_void_p), ("pair_count", C.c_void_p), ("chain_buf", C.c_void_p),
+                ("n_chains", C.c_int64), ("max_lag", C.c_int32), ("buf_len", C.c_int32)]
 
 
 class nk_sweep_t(C.Structure):
@@ -83,6 +90,11 @@ SYMBOLS = {
     "nk_forces_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_int64, C.c_void_p, C.c_int32]),
     "nk_stats_partial": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_double, C.c_void_p]),
     "nk_stats_finalize": (C.c_int, [C.POINTER(C.c_double), C.c_double, C.c_int64, C.c_int64, C.POINTER(C.c_double)]),
+    "nk_online_stats_update": (C.c_int, [C.c_void_p, C.POINTER(nk_online_stats_t), C.POINTER(nk_online_stats_t), C.c_void_p, C.c_int32,
+                                         C.c_int64, C.c_double]),
+    "nk_online_stats_summary": (C.c_int, [C.c_void_p, C.POINTER(nk_online_stats_t), C.c_int32, C.c_double, C.c_double, C.c_void_p]),
+    "nk_online_stats_finalize": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int64, C.c_int64, C.c_int32,
+                                           C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "nk_ctx_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32,
                                 C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_uint64, C.c_uint64]),
     "nk_ctx_destroy": (None, [C.c_void_p]),

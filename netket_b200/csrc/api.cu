@@ -49,6 +49,10 @@ int localop_conn(cudaStream_t stream, const nk_localop_t &op, const int8_t *x, i
 int stats_partial(cudaStream_t stream, const void *data, int32_t dtype, int64_t n_chains, int64_t L, int32_t phase, double shift,
                   double *out);
 int stats_finalize(const double *p, double mean, int64_t n_chains, int64_t L, double *out);
+int online_stats_update(cudaStream_t stream, const nk_online_stats_t *in, const nk_online_stats_t *out, const void *data, int32_t dtype,
+                        int64_t n, double decay);
+int online_stats_summary(cudaStream_t stream, const nk_online_stats_t *s, int32_t phase, double gmean, double mbar, double *out);
+int online_stats_finalize(const double *p0, const double *p1, int64_t n_chains, int64_t n_samples, int32_t L, double *o, double *acf);
 int random_state(cudaStream_t stream, int8_t *sigma, int64_t B, int32_t N, int32_t n_down, uint64_t seed, uint64_t chain_offset);
 int64_t theta_gemm_workspace_bytes(const nk_rbm_t &rbm, int64_t B);
 int theta_gemm(cudaStream_t stream, const nk_rbm_t &rbm, const int8_t *sigma, int64_t B, void *theta_out, void *workspace);
@@ -371,6 +375,46 @@ int nk_stats_partial(void *stream, const void *data, int32_t dtype, int64_t n_ch
   NK_CHECK_ARG(phase == 0 || phase == 1, "nk_stats_partial: phase must be 0 or 1");
   NK_CHECK_ARG(n_chains * L == 0 || data, "nk_stats_partial: NULL data");
   return stats_partial((cudaStream_t)stream, data, dtype, n_chains, L, phase, shift, partials_out);
+}
+
+static int online_state_ok(const nk_online_stats_t *s, const char *who) {
+  NK_CHECK_ARG(s, "%s: NULL state", who);
+  NK_CHECK_ARG(s->n_chains >= 0 && s->max_lag >= 0 && s->max_lag <= NK_ONLINE_MAX_LAG, "%s: bad n_chains / max_lag (max_lag <= %d)", who,
+               NK_ONLINE_MAX_LAG);
+  NK_CHECK_ARG(s->buf_len >= 0 && s->buf_len <= s->max_lag, "%s: buf_len must lie in [0, max_lag]", who);
+  if (s->n_chains > 0) {
+    NK_CHECK_ARG(s->chain_count && s->chain_mean && s->chain_M2, "%s: NULL per-chain array", who);
+    NK_CHECK_ARG(s->max_lag == 0 || (s->cross_sum && s->m1_sum && s->m2_sum && s->pair_count && s->chain_buf), "%s: NULL lag array", who);
+  }
+  return NK_OK;
+}
+
+int nk_online_stats_update(void *stream, const nk_online_stats_t *in, const nk_online_stats_t *out, const void *data, int32_t dtype,
+                           int64_t n, double decay) {
+  if (int rc = online_state_ok(in, "nk_online_stats_update")) return rc;
+  if (int rc = online_state_ok(out, "nk_online_stats_update")) return rc;
+  NK_CHECK_ARG(dtype == NK_F32 || dtype == NK_F64, "nk_online_stats_update: bad dtype");
+  NK_CHECK_ARG(in->n_chains == out->n_chains && in->max_lag == out->max_lag, "nk_online_stats_update: in / out shapes differ");
+  NK_CHECK_ARG(n >= 1, "nk_online_stats_update: the batch must hold at least one sample per chain");
+  NK_CHECK_ARG(decay > 0.0 && decay <= 1.0, "nk_online_stats_update: decay must lie in (0, 1]");
+  if (in->n_chains == 0) return NK_OK;
+  NK_CHECK_ARG(data, "nk_online_stats_update: NULL data");
+  return online_stats_update((cudaStream_t)stream, in, out, data, dtype, n, decay);
+}
+
+int nk_online_stats_summary(void *stream, const nk_online_stats_t *state, int32_t phase, double gmean, double mbar, double *sums_out) {
+  if (int rc = online_state_ok(state, "nk_online_stats_summary")) return rc;
+  NK_CHECK_ARG(phase == 0 || phase == 1, "nk_online_stats_summary: phase must be 0 or 1");
+  NK_CHECK_ARG(sums_out, "nk_online_stats_summary: NULL output");
+  return online_stats_summary((cudaStream_t)stream, state, phase, gmean, mbar, sums_out);
+}
+
+int nk_online_stats_finalize(const double *phase0_host, const double *phase1_host, int64_t n_chains_total, int64_t n_samples_total,
+                             int32_t max_lag, double *out_host, double *acf_host) {
+  NK_CHECK_ARG(phase0_host && phase1_host && out_host, "nk_online_stats_finalize: NULL argument");
+  NK_CHECK_ARG(n_chains_total > 0 && n_samples_total >= 0 && max_lag >= 0 && max_lag <= NK_ONLINE_MAX_LAG,
+               "nk_online_stats_finalize: bad arguments");
+  return online_stats_finalize(phase0_host, phase1_host, n_chains_total, n_samples_total, max_lag, out_host, acf_host);
 }
 
 int nk_stats_finalize(const double *sums_host, double mean, int64_t n_chains_total, int64_t L, double *out_host) {

@@ -115,3 +115,222 @@ def statistics(data):
         _lib.check(_lib.lib().nk_stats_partial(st, _lib.ptr(data), code, n_chains, L, 1, mean, _lib.ptr(part)))
         _allreduce(part)
     return finalize(part.tolist(), mean, n_chains_total, L)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Streaming statistics (netket/_src/stats/online_stats/*): the accumulator behind thermalise_mcmc,
+# check_mc_convergence and expect_to_precision.
+# ------------------------------------------------------------------------------------------------------------------
+_ONLINE_FIELDS = ("_chain_count", "_chain_mean", "_chain_M2", "_cross_sum", "_m1_sum", "_m2_sum", "_pair_count", "_chain_buf")
+
+
+class OnlineStats:
+    """``OnlineStats`` (accumulator.py:31-447): per-chain Welford state and the autocovariance at lags ``0..max_lag``,
+    updated batch by batch on the GPU (nk_online_stats_update, one warp per chain).  The fields carry the reference's
+    names and shapes; they are float64 device tensors (the reference keeps ``_chain_mean`` in the data's dtype).  Under
+    torch.distributed every rank holds its own chains; the derived quantities all-reduce ``4 + max_lag + 4`` doubles.
+    """
+
+    def __init__(self, n_chains, dtype=None, *, decay=None, max_lag=64, device=None):
+        from .utils import default_device
+
+        max_lag = int(max_lag)
+        if not 0 <= max_lag <= _lib.NK_ONLINE_MAX_LAG:
+            raise ValueError(f"max_lag must lie in [0, {_lib.NK_ONLINE_MAX_LAG}]")
+        if decay is not None and not 0.0 < float(decay) <= 1.0:
+            raise ValueError("decay must lie in (0, 1]")
+        dev = torch.device(device) if device is not None else default_device()
+        acf_len = max_lag + 1 if max_lag > 0 else 0
+        self.max_lag = max_lag
+        self._decay = decay
+        z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=dev)  # noqa: E731
+        self._chain_count, self._chain_mean, self._chain_M2 = z(n_chains), z(n_chains), z(n_chains)
+        self._cross_sum, self._m1_sum, self._m2_sum, self._pair_count = (z(n_chains, acf_len) for _ in range(4))
+        self._chain_buf = z(n_chains, max_lag)
+        self._buf_len = 0
+        self._n_samples_total = 0  # of this rank
+        self._summary = None
+
+    # ------------------------------------------------------------------ construction / update
+    @classmethod
+    def from_data(cls, data, *, decay=None, max_lag=64):
+        data = _as_device_2d(data)
+        return cls(data.shape[0], data.dtype, decay=decay, max_lag=max_lag, device=data.device).update(data)
+
+    def replace(self, **kw):
+        new = OnlineStats.__new__(OnlineStats)
+        new.__dict__.update(self.__dict__)
+        new.__dict__.update(kw)
+        new._summary = None
+        return new
+
+    def _c_struct(self):
+        p = lambda t: _lib.ptr(t) if t.numel() else None  # noqa: E731
+        return _lib.nk_online_stats_t(p(self._chain_count), p(self._chain_mean), p(self._chain_M2), p(self._cross_sum), p(self._m1_sum),
+                                      p(self._m2_sum), p(self._pair_count), p(self._chain_buf), self.n_chains, self.max_lag, self._buf_len)
+
+    def update(self, data, *, inplace=False):
+        """Merge a batch ``(n_chains, n)`` (or ``(n,)`` for one chain) and return the updated accumulator
+        (accumulator.py:166-221).  ``inplace=True`` reuses this object's buffers (the streaming loops do)."""
+        data = _as_device_2d(data)
+        if data.ndim != 2:
+            raise ValueError(f"data must be 1D or 2D, got {data.ndim}D")
+        n_chains_new, n = data.shape
+        if n_chains_new != self.n_chains:
+            raise ValueError(f"Number of chains changed: expected {self.n_chains}, got {n_chains_new}")
+        dev = self._chain_count.device
+        if data.device != dev:
+            raise ValueError("data lives on another device than the accumulator")
+        out = self if inplace else self.replace(**{f: torch.empty_like(getattr(self, f)) for f in _ONLINE_FIELDS})
+        with torch.cuda.device(dev):
+            a, b = self._c_struct(), out._c_struct()
+            _lib.check(_lib.lib().nk_online_stats_update(_lib.stream_ptr(dev), C.byref(a), C.byref(b), _lib.ptr(data),
+                                                         _lib.dtype_code(data.dtype), n, 1.0 if self._decay is None else float(self._decay)))
+        out._buf_len = min(self._buf_len + n, self.max_lag)
+        out._n_samples_total = self._n_samples_total + n_chains_new * n
+        out._summary = None
+        return out
+
+    # ------------------------------------------------------------------ derived quantities
+    @property
+    def n_chains(self):
+        return self._chain_mean.shape[0]
+
+    @property
+    def chain_means(self):
+        return self._chain_mean
+
+    @property
+    def decay(self):
+        return 1.0 if self._decay is None else self._decay
+
+    def _summarise(self):
+        if self._summary is not None:
+            return self._summary
+        dev = self._chain_count.device
+        n_lag = self.max_lag + 1 if self.max_lag > 0 else 0
+        p0 = torch.zeros(5, dtype=torch.float64, device=dev)
+        p1 = torch.zeros(_lib.NK_ONLINE_NSUM + n_lag, dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            st, s = _lib.stream_ptr(dev), self._c_struct()
+            _lib.check(_lib.lib().nk_online_stats_summary(st, C.byref(s), 0, 0.0, 0.0, _lib.ptr(p0)))
+            p0[3] = float(self.n_chains)
+            p0[4] = float(self._n_samples_total)
+            _allreduce(p0)
+            h0 = p0.tolist()
+            n_chains, n_samples = int(round(h0[3])), int(round(h0[4]))
+            gmean = h0[1] / h0[0] if h0[0] > 0 else 0.0
+            mbar = h0[2] / n_chains if n_chains > 0 else 0.0
+            _lib.check(_lib.lib().nk_online_stats_summary(st, C.byref(s), 1, gmean, mbar, _lib.ptr(p1)))
+            _allreduce(p1)
+            h1 = p1.tolist()
+        self._summary = online_finalize(h0[:3], h1, n_chains, n_samples, self.max_lag)
+        return self._summary
+
+    mean = property(lambda self: self._summarise()["out"][0], doc="count-weighted mean of the chain means (accumulator.py:240-250)")
+    variance = property(lambda self: self._summarise()["out"][2], doc="accumulator.py:252-263")
+    tau_corr = property(lambda self: self._summarise()["out"][3], doc="ACF-based if available, else batch (accumulator.py:265-271)")
+    R_hat = property(lambda self: self._summarise()["out"][4], doc="accumulator.py:379-395")
+    tau_corr_batch = property(lambda self: self._summarise()["out"][5], doc="accumulator.py:273-309")
+    tau_corr_acf = property(lambda self: self._summarise()["out"][6], doc="Geyer IPS + IMS (accumulator.py:311-351)")
+    error_of_mean = property(lambda self: self._summarise()["out"][1], doc="accumulator.py:430-447")
+
+    @property
+    def acf(self):
+        """Normalised autocorrelation function averaged over chains, ``(max_lag + 1,)`` NumPy array, or ``None``."""
+        return self._summarise()["acf"]
+
+    @property
+    def n_samples(self):
+        """Samples accumulated over all ranks (never decayed)."""
+        return self._summarise()["n_samples"]
+
+    def get_stats(self):
+        s = self._summarise()
+        if s["empty"]:
+            return Stats()
+        o = s["out"]
+        return Stats(mean=o[0], error_of_mean=o[1], variance=o[2], tau_corr=o[3], R_hat=o[4])
+
+    def to_dict(self):
+        return self.get_stats().to_dict()
+
+    def to_compound(self):
+        return self.get_stats().to_compound()
+
+    def __repr__(self):
+        return repr(self.get_stats())
+
+
+def online_finalize(p0, p1, n_chains, n_samples, max_lag):
+    """Host arithmetic of the derived quantities (nk_online_stats_finalize) on the globally reduced sums of
+    nk_online_stats_summary: ``p0`` = 3 doubles of phase 0, ``p1`` = ``4 + max_lag + 1`` doubles of phase 1."""
+    n_lag = max_lag + 1 if max_lag > 0 else 0
+    a0 = (C.c_double * 3)(*[float(v) for v in p0])
+    a1 = (C.c_double * (_lib.NK_ONLINE_NSUM + n_lag))(*[float(v) for v in p1])
+    out = (C.c_double * _lib.NK_ONLINE_NOUT)()
+    acf = (C.c_double * max(n_lag, 1))()
+    _lib.check(_lib.lib().nk_online_stats_finalize(a0, a1, max(int(n_chains), 1), int(n_samples), int(max_lag), out, acf))
+    acf = np.array(acf[:n_lag])
+    return dict(out=list(out), acf=None if n_lag == 0 or np.isnan(acf[0]) else acf, n_chains=int(n_chains), n_samples=int(n_samples),
+                empty=float(p0[0]) == 0.0)
+
+
+def _as_device_2d(data):
+    if isinstance(data, OnlineStats):
+        raise TypeError("expected samples, got an accumulator")
+    data = getattr(data, "data", data)  # LocalEstimators wrapper
+    if not isinstance(data, torch.Tensor):
+        from .utils import default_device
+
+        data = torch.from_numpy(np.ascontiguousarray(np.asarray(data))).to(default_device())
+    _lib.require_cuda(data, "data")
+    if data.dtype not in (torch.float32, torch.float64):
+        raise TypeError("online statistics: float32 / float64 data only (real-parameter RBM => real local energies)")
+    if data.ndim == 1:
+        data = data[None, :]
+    return data.contiguous()
+
+
+def online_statistics(data, old_estimator=None, *, decay=None, max_lag=64, inplace=False):
+    """Functional API (operations.py:55-129): ``est = online_statistics(batch, est)``."""
+    data = _as_device_2d(data)
+    if old_estimator is None:
+        old_estimator = OnlineStats(data.shape[0], data.dtype, decay=decay, max_lag=max_lag, device=data.device)
+        inplace = True
+    return old_estimator.update(data, inplace=inplace)
+
+
+def expand_max_lag(estimator, new_max_lag):
+    """operations.py:132-192: lags ``0..old`` are kept, new lags start empty, the buffer grows on the left."""
+    old, new_max_lag = estimator.max_lag, int(new_max_lag)
+    if new_max_lag <= old:
+        raise ValueError(f"new_max_lag={new_max_lag} must be > current max_lag={old}")
+    if new_max_lag > _lib.NK_ONLINE_MAX_LAG:
+        raise ValueError(f"max_lag must lie in [0, {_lib.NK_ONLINE_MAX_LAG}]")
+    extra = new_max_lag + 1 - (old + 1 if old > 0 else 0)
+    pad = torch.nn.functional.pad
+    return estimator.replace(max_lag=new_max_lag, _chain_buf=pad(estimator._chain_buf, (new_max_lag - old, 0)).contiguous(),
+                             **{f: pad(getattr(estimator, f), (0, extra)).contiguous()
+                                for f in ("_cross_sum", "_m1_sum", "_m2_sum", "_pair_count")})
+
+
+def thin_acf_by_2(estimator):
+    """operations.py:195-261: re-index the lag accumulators for a twice coarser sampling cadence."""
+    old = estimator.max_lag
+    if old < 2:
+        raise ValueError(f"max_lag={old} must be >= 2 to thin by 2")
+    new = old // 2
+    return estimator.replace(max_lag=new, _chain_buf=estimator._chain_buf[:, old - 2 * new::2].contiguous(), _buf_len=estimator._buf_len // 2,
+                             **{f: getattr(estimator, f)[:, 0:2 * new + 1:2].contiguous()
+                                for f in ("_cross_sum", "_m1_sum", "_m2_sum", "_pair_count")})
+
+
+def acf_window_saturated(estimator):
+    """True if the Geyer sequence found no non-positive pair inside the lag window (check_mc_convergence.py:243-255)."""
+    return bool(estimator._summarise()["out"][7])
+
+
+def tau_corr_reliable(estimator):
+    """check_mc_convergence.py:258-272: window not saturated and at least 50 effective samples per chain."""
+    return bool(estimator._summarise()["out"][8])

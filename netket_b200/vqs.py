@@ -278,6 +278,43 @@ class MCState:
         """<O> with MC statistics (state.py:695-712)."""
         return statistics(self.local_estimators(op))
 
+    # ------------------------------------------------------------------ streaming callers (SURVEY.md §8f rank 2)
+    def _sample_and_estimate(self, op, n_discard_per_chain=None):
+        """``self.sample(n_discard_per_chain=...); return self.local_estimators(op)`` as ONE fused launch."""
+        self._check_operator(op)
+        self.reset()
+        n_discard = self._n_discard if n_discard_per_chain is None else n_discard_per_chain
+        self._samples, eloc = self._run(self._chain_length, n_discard, operator=op)
+        self._eloc_cache = {id(op): eloc}
+        return eloc
+
+    def _set_sampler_keep_state(self, sampler, sampler_state):
+        """``self.sampler = sampler; self.sampler_state = sampler_state`` without drawing a fresh sampler state in between
+        (check_mc_convergence.py:132-134: same chains, another sweep size)."""
+        self._sampler = sampler
+        self.sampler_state = sampler_state
+        self.reset()
+
+    def check_mc_convergence(self, op, *, min_chain_length=50, max_chain_length=500, plot=False):
+        """state.py:829-844."""
+        from .convergence import check_mc_convergence
+
+        return check_mc_convergence(self, op, min_chain_length=min_chain_length, max_chain_length=max_chain_length, plot=plot)
+
+    def thermalise(self, op, *, min_chain_length=10, max_chain_length=100, rhat_tol=1.05, decay=0.9, patience=1, verbose=True,
+                   raise_on_failure=False):
+        """state.py:846-869."""
+        from .convergence import thermalise_mcmc
+
+        return thermalise_mcmc(self, op, min_chain_length=min_chain_length, max_chain_length=max_chain_length, rhat_tol=rhat_tol,
+                               decay=decay, patience=patience, verbose=verbose, raise_on_failure=raise_on_failure)
+
+    def expect_to_precision(self, op, *, atol=None, rtol=None, max_iter=10_000, max_lag=64, verbose=True):
+        """state.py:871-942."""
+        from .convergence import expect_to_precision
+
+        return expect_to_precision(self, op, atol=atol, rtol=rtol, max_iter=max_iter, max_lag=max_lag, verbose=verbose)
+
     def expect_and_forces(self, op, *, mutable=False):
         """``(Stats, forces)`` with ``forces[k] = < d log psi / d p_k * (E_loc - <E_loc>) >`` in the layout of
         ``self.parameters`` (netket/vqs/mc/mc_state/expect_forces.py:39-112).  The RBM's log-derivatives are closed

@@ -2,7 +2,8 @@
 own source can be executed in this container (jax is not installed) to generate golden vectors.
 
 Used only by tests/golden/make_golden.py.  Nothing here re-states reference logic: it re-states JAX semantics
-(``.at[].set``, ``vmap``, ``lax.select``, ``lax.cond``, ``jnp.where(size=, fill_value=)``) on top of NumPy.
+(``.at[].set`` / ``.add``, ``vmap``, ``lax.select``, ``lax.cond``, ``lax.scan``, ``lax.dynamic_slice_in_dim``,
+``jnp.where(size=, fill_value=)``) on top of NumPy.
 """
 
 import functools
@@ -26,6 +27,11 @@ class _AtIdx:
     def set(self, val):
         out = np.array(self.arr, copy=True).view(Arr)
         out[self.idx] = val
+        return out
+
+    def add(self, val):
+        out = np.array(self.arr, copy=True).view(Arr)
+        np.add.at(out, self.idx, val)
         return out
 
 
@@ -71,7 +77,7 @@ def _make_jnp():
     jnp = types.ModuleType("jax.numpy")
     for name in ("zeros", "ones", "full", "arange", "eye", "asarray", "array", "abs", "exp", "log", "log1p", "sqrt", "sum", "mean",
                  "var", "hstack", "broadcast_to", "expand_dims", "take", "signbit", "atleast_1d", "swapaxes", "dot",
-                 "isclose", "concatenate", "stack", "max", "min", "floor", "zeros_like"):
+                 "isclose", "concatenate", "stack", "max", "min", "floor", "zeros_like", "pad", "real", "minimum", "maximum", "all"):
         setattr(jnp, name, _lift(getattr(np, name)))
     jnp.where = _where
     jnp.clip = lambda a, min=None, max=None: _wrap(np.clip(a, min, max))  # noqa: A002  (jnp.clip(x, 0) == lower bound only)
@@ -143,6 +149,24 @@ def _cond(pred, true_fun, false_fun, *operands):
     return true_fun(*operands) if bool(pred) else false_fun(*operands)
 
 
+def _dynamic_slice_in_dim(operand, start_index, slice_size, axis=0):
+    """jax.lax.dynamic_slice_in_dim: the start index is clamped so that the slice stays inside the operand."""
+    n = np.asarray(operand).shape[axis]
+    start = int(np.clip(int(start_index), 0, n - slice_size))
+    idx = [slice(None)] * np.asarray(operand).ndim
+    idx[axis] = slice(start, start + slice_size)
+    return _wrap(np.asarray(operand)[tuple(idx)])
+
+
+def _scan(f, init, xs):
+    """jax.lax.scan for bodies that return (carry, None)."""
+    carry = init
+    for x in xs:
+        carry, y = f(carry, x)
+        assert y is None
+    return carry, None
+
+
 def make_jax():
     jax = types.ModuleType("jax")
     jnp = _make_jnp()
@@ -152,6 +176,8 @@ def make_jax():
     lax = types.ModuleType("jax.lax")
     lax.select = lambda m, a, b: _wrap(np.where(m, a, b))
     lax.cond = _cond
+    lax.scan = _scan
+    lax.dynamic_slice_in_dim = _dynamic_slice_in_dim
     jax.lax = lax
     jax.Array = np.ndarray
     tree_util = types.ModuleType("jax.tree_util")

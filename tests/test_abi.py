@@ -95,6 +95,27 @@ def test_argument_validation_happens_before_cuda(lib_built):
     assert L.nk_forces_workspace_bytes(C.byref(rbm), 1000) >= 1000 * 4 * 4
     big = _lib.nk_rbm_t(W=1, b=None, a=None, N=400, M=3200, dtype=0, reserved=0)
     assert L.nk_sweep_workspace_bytes(C.byref(big), 8) >= 8 * 3200 * 4 + 400 * 3200 * 4  # theta + the G table (several warps per chain)
+    # streaming statistics
+    st = _lib.nk_online_stats_t(1, 1, 1, None, None, None, None, None, 4, 8, 0)
+    assert L.nk_online_stats_update(None, C.byref(st), C.byref(st), 1, 1, 4, 1.0) == -1
+    assert b"NULL lag array" in L.nk_last_error()
+    st = _lib.nk_online_stats_t(1, 1, 1, 1, 1, 1, 1, 1, 4, 8, 9)
+    assert L.nk_online_stats_update(None, C.byref(st), C.byref(st), 1, 1, 4, 1.0) == -1
+    assert b"buf_len" in L.nk_last_error()
+    st = _lib.nk_online_stats_t(1, 1, 1, 1, 1, 1, 1, 1, 4, 8, 0)
+    assert L.nk_online_stats_update(None, C.byref(st), C.byref(st), 1, 1, 0, 1.0) == -1
+    assert b"at least one sample" in L.nk_last_error()
+    assert L.nk_online_stats_update(None, C.byref(st), C.byref(st), 1, 1, 4, 1.5) == -1
+    assert b"decay" in L.nk_last_error()
+    assert L.nk_online_stats_update(None, C.byref(st), C.byref(st), 1, 3, 4, 1.0) == -1
+    other = _lib.nk_online_stats_t(1, 1, 1, 1, 1, 1, 1, 1, 4, 16, 0)
+    assert L.nk_online_stats_update(None, C.byref(st), C.byref(other), 1, 1, 4, 1.0) == -1
+    assert b"shapes differ" in L.nk_last_error()
+    wide = _lib.nk_online_stats_t(1, 1, 1, 1, 1, 1, 1, 1, 4, 5000, 0)
+    assert L.nk_online_stats_summary(None, C.byref(wide), 0, 0.0, 0.0, 1) == -1
+    assert b"max_lag" in L.nk_last_error()
+    assert L.nk_online_stats_summary(None, C.byref(st), 2, 0.0, 0.0, 1) == -1
+    assert L.nk_online_stats_finalize(None, None, 1, 1, 0, None, None) == -1
 
 
 def _partials(x, mu):

@@ -39,6 +39,7 @@ def _partials(x, mu):
 
 def _worker(rank, ws, port, out):
     sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=ws)
@@ -97,6 +98,24 @@ def _worker(rank, ws, port, out):
     f_full = oforces.forces(samples, eloc, W, b, a)
     ref_vec = np.concatenate([f_full["W"].ravel(), f_full["b"], f_full["a"]])
     res["forces_ok"] = bool(np.allclose(sums.numpy() / eloc.size, ref_vec, rtol=1e-12, atol=1e-14))
+    # --- streaming statistics: every rank accumulates its own chains; the derived quantities come from all-reduced sums
+    # (3 doubles, then 4 + max_lag + 1), which equal those of one accumulator over all chains
+    from oracle import online_stats as oos
+    from test_online_stats import numpy_sums
+
+    e_full = e_mine = None
+    for lo, hi in [(0, 7), (7, 30), (30, 50)]:
+        e_full = oos.online_statistics(full[:, lo:hi], e_full, max_lag=12)
+        e_mine = oos.online_statistics(shard[:, lo:hi], e_mine, max_lag=12)
+    p0 = torch.from_numpy(np.concatenate([numpy_sums(e_mine), [float(e_mine.n_chains), float(e_mine.n_samples)]]))
+    nkstats._allreduce(p0)
+    h0 = p0.tolist()
+    p1 = torch.from_numpy(numpy_sums(e_mine, h0[1] / h0[0], h0[2] / h0[3]))
+    nkstats._allreduce(p1)
+    s = nkstats.online_finalize(h0[:3], p1.tolist(), int(h0[3]), int(h0[4]), 12)
+    want = [e_full.mean, e_full.error_of_mean, e_full.variance, e_full.tau_corr, e_full.R_hat, e_full.tau_corr_batch, e_full.tau_corr_acf]
+    res["online_ok"] = bool(np.allclose(s["out"][:7], want, rtol=1e-10, equal_nan=True) and np.allclose(s["acf"], e_full.acf, rtol=1e-10)
+                            and s["n_chains"] == 24 and s["n_samples"] == 24 * 50)
     out[rank] = res
     dist.barrier()
     dist.destroy_process_group()
@@ -114,5 +133,5 @@ def test_two_process_gloo():
         assert r["chains"] == (32, 16)
         assert r["rounded"] == (34, 17, True)
         assert r["default"] == 32  # 16 chains per rank
-        assert r["stats_ok"] and r["init_ok"] and r["chains_ok"] and r["forces_ok"]
+        assert r["stats_ok"] and r["init_ok"] and r["chains_ok"] and r["forces_ok"] and r["online_ok"]
     assert r0["seed"] == r1["seed"]
