@@ -33,15 +33,22 @@ __global__ void __launch_bounds__(OS_WARPS * 32) online_update_kernel(OsPtrs in,
   if (warp >= warps) return;
   double *z = os_smem + (size_t)warp * (L + OS_CHUNK);
   const int nk = L > 0 ? L + 1 : 0;
+  const bool single = n <= OS_CHUNK;  // the usual case (n = chain_length of one sampling call): one pass, sums stay in registers
+  const int rounds = (nk + 31) / 32;
   for (int64_t c = (int64_t)blockIdx.x * warps + warp; c < n_chains; c += (int64_t)gridDim.x * warps) {
     const T *x = data + c * n;
+    __syncwarp();
+    if (single)
+      for (int i = lane; i < (int)n; i += 32) z[L + i] = (double)x[i];
+    for (int i = lane; i < L; i += 32) z[i] = in.buf[c * L + i];
+    __syncwarp();
     // ---- parallel Welford merge of the batch (kernels.py:144-167)
     double s = 0.0;
-    for (int64_t i = lane; i < n; i += 32) s += (double)x[i];
+    for (int64_t i = lane; i < n; i += 32) s += single ? z[L + i] : (double)x[i];
     const double bm = warp_sum(s) / (double)n;
     double q = 0.0;
     for (int64_t i = lane; i < n; i += 32) {
-      const double d = (double)x[i] - bm;
+      const double d = (single ? z[L + i] : (double)x[i]) - bm;
       q += d * d;
     }
     q = warp_sum(q);
@@ -54,11 +61,34 @@ __global__ void __launch_bounds__(OS_WARPS * 32) online_update_kernel(OsPtrs in,
     }
     if (L == 0) continue;
     // ---- autocovariance sums (kernels.py:25-113)
-    __syncwarp();
-    for (int i = lane; i < L; i += 32) z[i] = in.buf[c * L + i];
     int first = L - buf_len;  // index in z of the oldest stored sample
-    const int rounds = (nk + 31) / 32;
-    // accumulators of lag k = lane + 32 r live in out.* between chunks: seed them with the decayed old sums
+    if (single) {
+      const int cn = (int)n;
+      for (int r = 0; r < rounds; ++r) {
+        const int k = lane + 32 * r;
+        if (k < nk) {
+          const double o_cross = in.cross[c * nk + k], o_m1 = in.m1[c * nk + k], o_m2 = in.m2[c * nk + k], o_np = in.pairs[c * nk + k];
+          double sc = 0.0, sl = 0.0, su = 0.0;
+          int t0 = first + k - L;  // first batch position whose partner t-k is a stored sample
+          t0 = t0 > 0 ? t0 : 0;
+          for (int t = t0; t < cn; ++t) {
+            const double cur = z[L + t], lag = z[L + t - k];
+            sc = fma(cur, lag, sc);
+            sl += lag;
+            su += cur;
+          }
+          const int np = cn - t0 > 0 ? cn - t0 : 0;
+          out.cross[c * nk + k] = fma(o_cross, decay, sc);
+          out.m1[c * nk + k] = fma(o_m1, decay, sl);
+          out.m2[c * nk + k] = fma(o_m2, decay, su);
+          out.pairs[c * nk + k] = fma(o_np, decay, (double)np);
+        }
+      }
+      for (int i = lane; i < L; i += 32) out.buf[c * L + i] = z[i + cn];  // the last L samples of z, right-aligned
+      continue;
+    }
+    // long batches: chunks of OS_CHUNK samples, the buffer rolling between them; the sums of lag k = lane + 32 r live in out.*
+    // between chunks, seeded with the decayed old sums
     for (int k = lane; k < nk; k += 32) {
       out.cross[c * nk + k] = in.cross[c * nk + k] * decay;
       out.m1[c * nk + k] = in.m1[c * nk + k] * decay;
@@ -73,7 +103,7 @@ __global__ void __launch_bounds__(OS_WARPS * 32) online_update_kernel(OsPtrs in,
         const int k = lane + 32 * r;
         if (k < nk) {
           double sc = 0.0, sl = 0.0, su = 0.0;
-          int t0 = first + k - L;  // first batch position whose partner t-k is a stored sample
+          int t0 = first + k - L;
           t0 = t0 > 0 ? t0 : 0;
           for (int t = t0; t < cn; ++t) {
             const double cur = z[L + t], lag = z[L + t - k];

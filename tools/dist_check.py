@@ -34,4 +34,24 @@ for dtype in (np.float64, np.float32):
         # chains are distinct across ranks (global chain index keys the stream)
         distinct = len({S[i * B].tobytes() for i in range(ws)}) == ws
         print(f"dist_check {np.dtype(dtype).name} ws={ws}: stats+grad {'OK' if ok else 'MISMATCH'}, distinct shards {distinct}, E = {st}")
+    # streaming statistics: every rank accumulates its own chains, the derived quantities all-reduce the summary sums
+    from netket_b200.stats import online_statistics
+    acc = None
+    batches = []
+    for it in range(3):
+        e = vs._sample_and_estimate(op, None if it == 0 else 0)
+        acc = online_statistics(e, acc, max_lag=16, inplace=True)
+        allb = [torch.empty_like(e) for _ in range(ws)]; dist.all_gather(allb, e); batches.append(torch.cat(allb).cpu().numpy())
+    got = [acc.mean, acc.error_of_mean, acc.variance, acc.tau_corr, acc.R_hat, acc.tau_corr_batch, acc.tau_corr_acf, acc.n_samples]
+    if rank == 0:
+        from oracle import online_stats as oos
+        ref = None
+        for bt in batches:
+            ref = oos.online_statistics(bt.astype(np.float64), ref, max_lag=16)
+        want = [ref.mean, ref.error_of_mean, ref.variance, ref.tau_corr, ref.R_hat, ref.tau_corr_batch, ref.tau_corr_acf, ref.n_samples]
+        ok = np.allclose(got, want, rtol=1e-9 if dtype == np.float64 else 1e-5) and np.allclose(acc.acf, ref.acf, rtol=1e-5, atol=1e-6)
+        print(f"dist_check {np.dtype(dtype).name} ws={ws}: online statistics over {ref.n_chains} chains {'OK' if ok else 'MISMATCH'}: {acc}")
+    st2 = vs.expect_to_precision(op, rtol=2e-3, max_iter=50, verbose=False)
+    if rank == 0:
+        print(f"dist_check expect_to_precision ws={ws}: {st2}, n_samples={st2.n_samples}")
 dist.barrier(); dist.destroy_process_group()
