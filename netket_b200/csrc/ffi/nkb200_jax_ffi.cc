@@ -165,3 +165,48 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(NkForces, ForcesImpl,
                                   .Ret<ffi::Buffer<ffi::F64>>()   // sums
                                   .Ret<ffi::Buffer<ffi::U8>>()    // workspace (nk_forces_workspace_bytes)
                                   .Attr<double>("mean"));
+
+// OnlineStats.update: the eight state arrays of the pytree in, the eight updated arrays out (`_update_arrays`,
+// netket/_src/stats/online_stats/kernels.py:116-190).  max_lag comes from the shapes, buf_len / decay are attributes.
+static ffi::Error OnlineUpdateImpl(cudaStream_t stream, ffi::Buffer<ffi::F64> count, ffi::Buffer<ffi::F64> mean, ffi::Buffer<ffi::F64> M2,
+                                   ffi::Buffer<ffi::F64> cross, ffi::Buffer<ffi::F64> m1, ffi::Buffer<ffi::F64> m2,
+                                   ffi::Buffer<ffi::F64> pairs, ffi::Buffer<ffi::F64> buf, ffi::AnyBuffer data,
+                                   ffi::Result<ffi::Buffer<ffi::F64>> count_o, ffi::Result<ffi::Buffer<ffi::F64>> mean_o,
+                                   ffi::Result<ffi::Buffer<ffi::F64>> M2_o, ffi::Result<ffi::Buffer<ffi::F64>> cross_o,
+                                   ffi::Result<ffi::Buffer<ffi::F64>> m1_o, ffi::Result<ffi::Buffer<ffi::F64>> m2_o,
+                                   ffi::Result<ffi::Buffer<ffi::F64>> pairs_o, ffi::Result<ffi::Buffer<ffi::F64>> buf_o, int32_t buf_len,
+                                   double decay) {
+  const int64_t n_chains = data.dimensions()[0], n = data.dimensions()[1];
+  const int32_t max_lag = (int32_t)buf.dimensions()[1];
+  nk_online_stats_t in{count.typed_data(), mean.typed_data(), M2.typed_data(), cross.typed_data(), m1.typed_data(),
+                       m2.typed_data(),    pairs.typed_data(), buf.typed_data(), n_chains,          max_lag,
+                       buf_len};
+  nk_online_stats_t out{count_o->typed_data(), mean_o->typed_data(), M2_o->typed_data(), cross_o->typed_data(), m1_o->typed_data(),
+                        m2_o->typed_data(),    pairs_o->typed_data(), buf_o->typed_data(), n_chains,            max_lag,
+                        buf_len};
+  const int rc = nk_online_stats_update(stream, &in, &out, data.untyped_data(), dtype_code(data.element_type()), n, decay);
+  return rc == NK_OK ? ffi::Error::Success() : fail();
+}
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(NkOnlineStatsUpdate, OnlineUpdateImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()   // _chain_count
+                                  .Arg<ffi::Buffer<ffi::F64>>()   // _chain_mean
+                                  .Arg<ffi::Buffer<ffi::F64>>()   // _chain_M2
+                                  .Arg<ffi::Buffer<ffi::F64>>()   // _cross_sum
+                                  .Arg<ffi::Buffer<ffi::F64>>()   // _m1_sum
+                                  .Arg<ffi::Buffer<ffi::F64>>()   // _m2_sum
+                                  .Arg<ffi::Buffer<ffi::F64>>()   // _pair_count
+                                  .Arg<ffi::Buffer<ffi::F64>>()   // _chain_buf
+                                  .Arg<ffi::AnyBuffer>()          // data (n_chains, n)
+                                  .Ret<ffi::Buffer<ffi::F64>>()
+                                  .Ret<ffi::Buffer<ffi::F64>>()
+                                  .Ret<ffi::Buffer<ffi::F64>>()
+                                  .Ret<ffi::Buffer<ffi::F64>>()
+                                  .Ret<ffi::Buffer<ffi::F64>>()
+                                  .Ret<ffi::Buffer<ffi::F64>>()
+                                  .Ret<ffi::Buffer<ffi::F64>>()
+                                  .Ret<ffi::Buffer<ffi::F64>>()
+                                  .Attr<int32_t>("buf_len")
+                                  .Attr<double>("decay"));
