@@ -231,6 +231,18 @@ int nk_forces_rbm(void *stream, const nk_rbm_t *rbm, const int8_t *samples, int6
                   double mean, double *sums, void *workspace, const void *tanh_theta);
 int nk_forces_finalize(void *stream, const double *sums, double scale, int64_t n, void *out, int32_t dtype);
 
+/* Quantum geometric tensor, matrix-free (QGTOnTheFly: netket/optimizer/qgt/qgt_onthefly_logic.py:33-43,
+ *   S v = O^H ((O v - mean(O v)) / n) + diag_shift v,   O[s, :] = d log psi(sigma_s) / d p  in closed form for the RBM).
+ *   nk_rbm_tanh_theta  out[Ns, M] (rbm dtype) = tanh(sigma W + b): what nk_sweep_t.tanh_out records, for samples drawn without it
+ *                      (theta GEMM + tanh in place).  workspace: nk_theta_gemm_workspace_bytes(rbm, Ns).
+ *   nk_rbm_jvp         y[Ns] (double) = O v.  `v` carries the tangent vector in the layout of the parameters ({V, v_b, v_a};
+ *                      b / a may be NULL like the parameters').  scratch: Ns * M elements of v's dtype (receives sigma V + v_b);
+ *                      workspace: nk_theta_gemm_workspace_bytes(v, Ns).
+ *   O^H w is nk_forces_rbm with `eloc = y`, `mean = mean(y)` (all-reduced), scaled by 1 / n_samples in nk_forces_finalize. */
+int nk_rbm_tanh_theta(void *stream, const nk_rbm_t *rbm, const int8_t *samples, int64_t Ns, void *out, void *workspace);
+int nk_rbm_jvp(void *stream, const nk_rbm_t *v, const int8_t *samples, int64_t Ns, const void *tanh_theta, double *y_out, void *scratch,
+               void *workspace);
+
 /* ---------------------------------------------------------------------------------------------
  * Host-buffer API: one VMC inner-loop step with HOST pointers (what bench.py's `e2e` times).
  * The context owns the device buffers (parameters, chains, operator tables, E_loc).

@@ -12,7 +12,7 @@ Scope: SURVEY.md §8 / DESIGN.md.  There is no CPU path: every numerical entry p
 (include/nkb200.h) and raises if it is missing.
 """
 
-from . import convergence, graph, hilbert, models, operator, sampler, serialization, stats, vqs  # noqa: F401
+from . import convergence, driver, graph, hilbert, models, operator, optimizer, sampler, serialization, stats, vqs  # noqa: F401
 from ._lib import NkError, LIB_PATH  # noqa: F401
 
 __version__ = "0.1.0"

@@ -49,6 +49,8 @@ int localop_conn(cudaStream_t stream, const nk_localop_t &op, const int8_t *x, i
 int stats_partial(cudaStream_t stream, const void *data, int32_t dtype, int64_t n_chains, int64_t L, int32_t phase, double shift,
                   double *out);
 int stats_finalize(const double *p, double mean, int64_t n_chains, int64_t L, double *out);
+int rbm_tanh_inplace(cudaStream_t stream, void *x, int32_t dtype, int64_t n);
+int rbm_jvp_dot(cudaStream_t stream, const nk_rbm_t &v, const int8_t *sigma, int64_t Ns, const void *t, const void *g, double *y);
 int online_stats_update(cudaStream_t stream, const nk_online_stats_t *in, const nk_online_stats_t *out, const void *data, int32_t dtype,
                         int64_t n, double decay);
 int online_stats_summary(cudaStream_t stream, const nk_online_stats_t *s, int32_t phase, double gmean, double mbar, double *out);
@@ -375,6 +377,27 @@ int nk_stats_partial(void *stream, const void *data, int32_t dtype, int64_t n_ch
   NK_CHECK_ARG(phase == 0 || phase == 1, "nk_stats_partial: phase must be 0 or 1");
   NK_CHECK_ARG(n_chains * L == 0 || data, "nk_stats_partial: NULL data");
   return stats_partial((cudaStream_t)stream, data, dtype, n_chains, L, phase, shift, partials_out);
+}
+
+int nk_rbm_tanh_theta(void *stream, const nk_rbm_t *rbm, const int8_t *samples, int64_t Ns, void *out, void *workspace) {
+  int rc = check_rbm(rbm, "nk_rbm_tanh_theta");
+  if (rc) return rc;
+  NK_CHECK_ARG(Ns >= 0, "nk_rbm_tanh_theta: Ns=%lld", (long long)Ns);
+  NK_CHECK_ARG(Ns == 0 || (samples && out), "nk_rbm_tanh_theta: NULL buffer");
+  rc = theta_gemm((cudaStream_t)stream, *rbm, samples, Ns, out, workspace);
+  if (rc) return rc;
+  return rbm_tanh_inplace((cudaStream_t)stream, out, rbm->dtype, Ns * (int64_t)rbm->M);
+}
+
+int nk_rbm_jvp(void *stream, const nk_rbm_t *v, const int8_t *samples, int64_t Ns, const void *tanh_theta, double *y_out, void *scratch,
+               void *workspace) {
+  int rc = check_rbm(v, "nk_rbm_jvp");
+  if (rc) return rc;
+  NK_CHECK_ARG(Ns >= 0, "nk_rbm_jvp: Ns=%lld", (long long)Ns);
+  NK_CHECK_ARG(Ns == 0 || (samples && tanh_theta && y_out && scratch), "nk_rbm_jvp: NULL buffer");
+  rc = theta_gemm((cudaStream_t)stream, *v, samples, Ns, scratch, workspace);  // sigma V + v_b on the tensor cores
+  if (rc) return rc;
+  return rbm_jvp_dot((cudaStream_t)stream, *v, samples, Ns, tanh_theta, scratch, y_out);
 }
 
 static int online_state_ok(const nk_online_stats_t *s, const char *who) {

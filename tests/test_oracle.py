@@ -255,3 +255,34 @@ def test_rbm_log_derivatives_match_finite_differences():
     Wp[1, 3] += h
     Wm[1, 3] -= h
     np.testing.assert_allclose(g_exact[1, 3], (energy(Wp) - energy(Wm)) / (2 * h), rtol=1e-6, atol=1e-8)
+
+
+def test_qgt_oracle_is_consistent():
+    """oracle/qgt.py: the Jacobian equals finite differences of logpsi, the dense S equals the reference's matrix-free recipe
+    (qgt_onthefly_logic.py:33-43), S is symmetric positive semi-definite and annihilates nothing it should not."""
+    from oracle import qgt as oqgt, rbm as orbm
+
+    rs = np.random.default_rng(5)
+    N, M = 6, 9
+    W, b, a = rs.normal(size=(N, M)) * 0.3, rs.normal(size=M) * 0.2, rs.normal(size=N) * 0.2
+    sig = (1 - 2 * rs.integers(0, 2, size=(64, N))).astype(np.int8)
+    O = oqgt.jacobian(sig, W, b, a)
+    p = np.concatenate([W.ravel(), b, a])
+
+    def lp(q):
+        return orbm.logpsi(sig, q[:N * M].reshape(N, M), q[N * M:N * M + M], q[N * M + M:])
+
+    for k in (0, 7, N * M + 3, N * M + M + 2):
+        e = np.zeros_like(p)
+        e[k] = 1e-6
+        np.testing.assert_allclose((lp(p + e) - lp(p - e)) / 2e-6, O[:, k], atol=1e-8)
+    S = oqgt.qgt_dense(sig, W, b, a, 0.0)
+    np.testing.assert_allclose(S, S.T, atol=1e-14)
+    assert np.linalg.eigvalsh(S).min() > -1e-12
+    v = rs.normal(size=p.size)
+    np.testing.assert_allclose(S @ v + 0.01 * v, oqgt.mat_vec(sig, W, b, a, v, 0.01), atol=1e-13)
+    g = rs.normal(size=p.size)
+    x = oqgt.sr_solve(sig, W, b, a, g, 0.01)
+    np.testing.assert_allclose(oqgt.mat_vec(sig, W, b, a, x, 0.01), g, atol=1e-10)
+    # without biases the Jacobian keeps the kernel block only
+    assert oqgt.jacobian(sig, W, None, None).shape == (64, N * M)
