@@ -236,12 +236,12 @@ int nk_forces_finalize(void *stream, const double *sums, double scale, int64_t n
  *   nk_rbm_tanh_theta  out[Ns, M] (rbm dtype) = tanh(sigma W + b): what nk_sweep_t.tanh_out records, for samples drawn without it
  *                      (theta GEMM + tanh in place).  workspace: nk_theta_gemm_workspace_bytes(rbm, Ns).
  *   nk_rbm_jvp         y[Ns] (double) = O v.  `v` carries the tangent vector in the layout of the parameters ({V, v_b, v_a};
- *                      b / a may be NULL like the parameters').  scratch: Ns * M elements of v's dtype (receives sigma V + v_b);
+ *                      b / a may be NULL like the parameters').  y_sum_out (1 double, device, optional) receives sum_s y[s].  scratch: Ns * M elements of v's dtype (receives sigma V + v_b);
  *                      workspace: nk_theta_gemm_workspace_bytes(v, Ns).
  *   O^H w is nk_forces_rbm with `eloc = y`, `mean = mean(y)` (all-reduced), scaled by 1 / n_samples in nk_forces_finalize. */
 int nk_rbm_tanh_theta(void *stream, const nk_rbm_t *rbm, const int8_t *samples, int64_t Ns, void *out, void *workspace);
-int nk_rbm_jvp(void *stream, const nk_rbm_t *v, const int8_t *samples, int64_t Ns, const void *tanh_theta, double *y_out, void *scratch,
-               void *workspace);
+int nk_rbm_jvp(void *stream, const nk_rbm_t *v, const int8_t *samples, int64_t Ns, const void *tanh_theta, double *y_out,
+               double *y_sum_out, void *scratch, void *workspace);
 
 /* ---------------------------------------------------------------------------------------------
  * Host-buffer API: one VMC inner-loop step with HOST pointers (what bench.py's `e2e` times).

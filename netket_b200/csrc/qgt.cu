@@ -23,8 +23,10 @@ __global__ void __launch_bounds__(256) tanh_inplace_kernel<float>(float *__restr
 // y[s] = sum_j t[s, j] g[s, j] + sum_i sigma[s, i] va[i]; one warp per sample, double accumulation
 template <typename T>
 __global__ void __launch_bounds__(256) jvp_dot_kernel(const T *__restrict__ t, const T *__restrict__ g, const int8_t *__restrict__ sigma,
-                                                      const T *__restrict__ va, int N, int M, int64_t Ns, double *__restrict__ y) {
+                                                      const T *__restrict__ va, int N, int M, int64_t Ns, double *__restrict__ y,
+                                                      double *__restrict__ y_sum) {
   const int lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+  double total = 0.0;
   for (int64_t s = (int64_t)blockIdx.x * warps + (threadIdx.x >> 5); s < Ns; s += (int64_t)gridDim.x * warps) {
     const T *tr = t + s * M, *gr = g + s * M;
     double acc = 0.0;
@@ -35,7 +37,9 @@ __global__ void __launch_bounds__(256) jvp_dot_kernel(const T *__restrict__ t, c
     }
     acc = warp_sum(acc);
     if (lane == 0) y[s] = acc;
+    total += acc;
   }
+  if (y_sum && lane == 0 && total != 0.0) atomicAdd(y_sum, total);  // sum over the device's samples (mean(O v) needs it)
 }
 
 static int grid_for(int64_t units, int per_block, int waves) {
@@ -54,13 +58,15 @@ int rbm_tanh_inplace(cudaStream_t stream, void *x, int32_t dtype, int64_t n) {
   return NK_OK;
 }
 
-int rbm_jvp_dot(cudaStream_t stream, const nk_rbm_t &v, const int8_t *sigma, int64_t Ns, const void *t, const void *g, double *y) {
+int rbm_jvp_dot(cudaStream_t stream, const nk_rbm_t &v, const int8_t *sigma, int64_t Ns, const void *t, const void *g, double *y,
+                double *y_sum) {
+  if (y_sum) NK_CUDA_OK(cudaMemsetAsync(y_sum, 0, sizeof(double), stream));
   if (Ns == 0) return NK_OK;
   const int grid = grid_for(Ns, 8, 16);
   if (v.dtype == NK_F32)
-    jvp_dot_kernel<float><<<grid, 256, 0, stream>>>((const float *)t, (const float *)g, sigma, (const float *)v.a, v.N, v.M, Ns, y);
+    jvp_dot_kernel<float><<<grid, 256, 0, stream>>>((const float *)t, (const float *)g, sigma, (const float *)v.a, v.N, v.M, Ns, y, y_sum);
   else
-    jvp_dot_kernel<double><<<grid, 256, 0, stream>>>((const double *)t, (const double *)g, sigma, (const double *)v.a, v.N, v.M, Ns, y);
+    jvp_dot_kernel<double><<<grid, 256, 0, stream>>>((const double *)t, (const double *)g, sigma, (const double *)v.a, v.N, v.M, Ns, y, y_sum);
   NK_LAUNCH_OK();
   return NK_OK;
 }

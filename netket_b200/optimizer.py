@@ -177,13 +177,11 @@ class QGTOnTheFly:
         vr = _lib.nk_rbm_t(W=_lib.ptr(V), b=_lib.ptr(vb.contiguous()) if vb is not None else None,
                            a=_lib.ptr(va.contiguous()) if va is not None else None, N=N, M=M, dtype=_lib.dtype_code(V.dtype), reserved=0)
         sums = torch.empty(N * M + M + N, dtype=torch.float64, device=dev)
-        part = torch.zeros(_lib.NK_STATS_NPARTIAL, dtype=torch.float64, device=dev)
+        head = torch.empty(1, dtype=torch.float64, device=dev)
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
             _lib.check(L.nk_rbm_jvp(st, C.byref(vr), _lib.ptr(self._s8), self._Ns, _lib.ptr(self._tanh), _lib.ptr(self._y),
-                                    _lib.ptr(self._scratch), _lib.ptr(self._ws)))
-            _lib.check(L.nk_stats_partial(st, _lib.ptr(self._y), _lib.NK_F64, 1, self._Ns, 0, 0.0, _lib.ptr(part)))  # sum of y
-            head = part[:1].clone()
+                                    _lib.ptr(head), _lib.ptr(self._scratch), _lib.ptr(self._ws)))
             _allreduce(head)
             mean = float(head.item()) / self._n_total
             _lib.check(L.nk_forces_rbm(st, C.byref(self._rbm), _lib.ptr(self._s8), self._Ns, _lib.ptr(self._y), _lib.NK_F64, mean,
