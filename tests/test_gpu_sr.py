@@ -141,3 +141,43 @@ def test_driver_api(cuda):
     with pytest.warns(UserWarning, match="rank deficient"):
         small, Hs = make_state(nk, n_chains=16, n_samples=16)
         nk.driver.VMC(Hs, nk.optimizer.Sgd(0.1), variational_state=small, preconditioner=nk.optimizer.SR())
+
+
+@pytest.mark.parametrize("N,M,B,dtype,biases", [
+    (10, 20, 300, np.float32, (True, True)),      # tcgen05 with the dot fused into the epilogue, one column tile, 128-bit loads
+    (20, 320, 1000, np.float32, (True, True)),    # two column tiles (two CTAs add into y[row])
+    (100, 400, 4096, np.float32, (True, True)),   # cfg-3 shape: the second tile ends in a 16-column chunk beyond M
+    (33, 52, 257, np.float32, (False, True)),     # odd N, no hidden bias
+    (16, 18, 130, np.float32, (True, False)),     # M % 4 != 0: scalar loads; no visible bias
+    (6, 12, 200, np.float32, (True, True)),       # M < 16: GEMM on CUDA cores + separate row dot
+    (20, 40, 500, np.float64, (True, True)),      # fp64: DMMA GEMM + separate row dot
+])
+def test_rbm_jvp_matches_oracle_jacobian(cuda, N, M, B, dtype, biases):
+    """nk_rbm_jvp through the C ABI: y = O v and its sum, against the oracle's Jacobian (every kernel route of the product)."""
+    import ctypes as C
+    from netket_b200 import _lib
+
+    rs = np.random.default_rng(N * 1000 + M)
+    W, b, a = rs.normal(size=(N, M)) * 0.2, rs.normal(size=M) * 0.2, rs.normal(size=N) * 0.2
+    V, vb, va = rs.normal(size=(N, M)), rs.normal(size=M) if biases[0] else None, rs.normal(size=N) if biases[1] else None
+    sig = (1 - 2 * rs.integers(0, 2, size=(B, N))).astype(np.int8)
+    O = oqgt.jacobian(sig, W, b, a)                       # columns [W | b | a]
+    v = np.concatenate([V.ravel(), vb if vb is not None else np.zeros(M), va if va is not None else np.zeros(N)])
+    want = O @ v
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    dev = lambda x: None if x is None else torch.from_numpy(np.ascontiguousarray(x)).to(device=cuda, dtype=tdt)  # noqa: E731
+    tanh = dev(np.tanh(sig.astype(np.float64) @ W + b))
+    Vd, vbd, vad, s8 = dev(V), dev(vb), dev(va), torch.from_numpy(sig).to(cuda)
+    vr = _lib.nk_rbm_t(W=_lib.ptr(Vd), b=_lib.ptr(vbd) if vbd is not None else None, a=_lib.ptr(vad) if vad is not None else None, N=N, M=M,
+                       dtype=_lib.dtype_code(tdt), reserved=0)
+    L = _lib.lib()
+    ws = torch.empty(max(int(L.nk_theta_gemm_workspace_bytes(C.byref(vr), B)), 1), dtype=torch.uint8, device=cuda)
+    scratch = torch.empty((B, M), dtype=tdt, device=cuda)
+    y = torch.full((B,), 7.0, dtype=torch.float64, device=cuda)
+    ysum = torch.full((1,), 7.0, dtype=torch.float64, device=cuda)
+    with torch.cuda.device(cuda):
+        _lib.check(L.nk_rbm_jvp(_lib.stream_ptr(cuda), C.byref(vr), _lib.ptr(s8), B, _lib.ptr(tanh), _lib.ptr(y), _lib.ptr(ysum),
+                                _lib.ptr(scratch), _lib.ptr(ws)))
+    tol = (1e-11 if dtype == np.float64 else 3e-6) * np.abs(want).max() * np.sqrt(M)
+    np.testing.assert_allclose(y.cpu().numpy(), want, rtol=0, atol=tol)
+    np.testing.assert_allclose(ysum.item(), want.sum(), rtol=0, atol=tol * np.sqrt(B) * 4)
