@@ -50,8 +50,6 @@ int stats_partial(cudaStream_t stream, const void *data, int32_t dtype, int64_t 
                   double *out);
 int stats_finalize(const double *p, double mean, int64_t n_chains, int64_t L, double *out);
 int rbm_tanh_inplace(cudaStream_t stream, void *x, int32_t dtype, int64_t n);
-int theta_gemm_dot(cudaStream_t stream, const nk_rbm_t &v, const int8_t *sigma, int64_t B, const void *dot, double *y, double *y_sum,
-                   void *workspace);
 int rbm_jvp_dot(cudaStream_t stream, const nk_rbm_t &v, const int8_t *sigma, int64_t Ns, const void *t, const void *g, double *y,
                 double *y_sum);
 int online_stats_update(cudaStream_t stream, const nk_online_stats_t *in, const nk_online_stats_t *out, const void *data, int32_t dtype,
@@ -398,8 +396,6 @@ int nk_rbm_jvp(void *stream, const nk_rbm_t *v, const int8_t *samples, int64_t N
   if (rc) return rc;
   NK_CHECK_ARG(Ns >= 0, "nk_rbm_jvp: Ns=%lld", (long long)Ns);
   NK_CHECK_ARG(Ns == 0 || (samples && tanh_theta && y_out && scratch), "nk_rbm_jvp: NULL buffer");
-  rc = theta_gemm_dot((cudaStream_t)stream, *v, samples, Ns, tanh_theta, y_out, y_sum_out, workspace);  // fp32: dot fused into the GEMM
-  if (rc <= 0) return rc;
   rc = theta_gemm((cudaStream_t)stream, *v, samples, Ns, scratch, workspace);  // sigma V + v_b on the tensor cores
   if (rc) return rc;
   return rbm_jvp_dot((cudaStream_t)stream, *v, samples, Ns, tanh_theta, scratch, y_out, y_sum_out);

@@ -83,13 +83,8 @@ struct TcArgs {
   int64_t B;
   int N, M, kpad, nt, NT, sbo, tmem_cols, acc_cols, vec_ok;
   uint32_t part_bytes, img_bytes;
-  // DOT epilogue (nk_rbm_jvp): instead of storing the tile, y[row] += sum_j (acc + bias)_j dot[row, j] (+ sigma_row . va once)
-  const float *dot;
-  const float *va;
-  double *y, *y_sum;
 };
 
-template <bool DOT>
 __global__ void __launch_bounds__(128, 1) theta_tc_kernel(const __grid_constant__ TcArgs p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char *b_img = smem;                          // 3 parts, K-major core-matrix layout
@@ -199,71 +194,6 @@ __global__ void __launch_bounds__(128, 1) theta_tc_kernel(const __grid_constant_
     // ---- this block: wait for its accumulator, epilogue: warp w owns TMEM lanes 32w..32w+31 = rows 32w..32w+31
     wait_bar(bar_mma + buf, (uint32_t)((it >> 1) & 1));
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if constexpr (DOT) {
-      // fused row dot: this thread owns row `row`; its slice of dot[row, :] is fetched one 32-column chunk ahead of the
-      // accumulator chunk it multiplies, so that the global loads overlap the TMEM loads and the FMAs
-      const int64_t row = rb * 128 + tid;
-      const bool live = row < p.B;
-      const float *drow = p.dot + row * p.M + n0;
-      const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * p.acc_cols);
-      float dn[32];
-      auto fetch = [&](int c0) {
-        const int width = min(32, p.NT - c0);
-        if (live && p.vec_ok && n0 + c0 + width <= p.M) {
-#pragma unroll
-          for (int e = 0; e < 32; e += 4) {
-            const float4 v = e < width ? __ldg(reinterpret_cast<const float4 *>(drow + c0 + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            dn[e] = v.x, dn[e + 1] = v.y, dn[e + 2] = v.z, dn[e + 3] = v.w;
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) dn[e] = (live && e < width && n0 + c0 + e < p.M) ? __ldg(drow + c0 + e) : 0.0f;
-        }
-      };
-      fetch(0);
-      double rowacc = 0.0;
-      for (int c0 = 0; c0 < p.NT; c0 += 32) {
-        float dc[32];
-#pragma unroll
-        for (int e = 0; e < 32; ++e) dc[e] = dn[e];
-        if (c0 + 32 < p.NT) fetch(c0 + 32);
-        uint32_t r[32];
-        const int width = min(32, p.NT - c0);
-        if (width == 32)
-          tmem_ld32(lane_addr + c0, r);
-        else
-          tmem_ld16(lane_addr + c0, r);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        float part = 0.0f;
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const int j = n0 + c0 + e;
-          if (e < width) {  // columns beyond M hold zero weights and a zero dot value
-            const float bj = (p.bias != nullptr && j < p.M) ? __ldg(p.bias + j) : 0.0f;
-            part = fmaf(__uint_as_float(r[e]) + bj, dc[e], part);
-          }
-        }
-        rowacc += (double)part;
-      }
-      if (live) {
-        if (tile == 0 && p.va != nullptr) {
-          const int8_t *srow = p.sigma + row * p.N;
-          float part = 0.0f;
-          for (int i = 0; i < p.N; ++i) part = fmaf((float)srow[i], __ldg(p.va + i), part);
-          rowacc += (double)part;
-        }
-        if (p.nt == 1)
-          p.y[row] = rowacc;
-        else
-          atomicAdd(p.y + row, rowacc);  // the two column tiles of a row live in two CTAs; y is zeroed by the host
-      } else {
-        rowacc = 0.0;
-      }
-      if (p.y_sum != nullptr) {
-        const double tot = warp_sum(rowacc);
-        if ((tid & 31) == 0 && tot != 0.0) atomicAdd(p.y_sum, tot);
-      }
-    } else
     {
       const int64_t row = rb * 128 + tid;
       float *out = p.theta + row * p.M;
@@ -370,58 +300,11 @@ int theta_gemm(cudaStream_t stream, const nk_rbm_t &rbm, const int8_t *sigma, in
   if (a.vec_ok && rbm.M % 8 == 0 && g.NT % 8 == 0 && (reinterpret_cast<uintptr_t>(theta_out) & 31) == 0) a.vec_ok = 2;
   a.part_bytes = (uint32_t)g.part_bytes;
   a.img_bytes = (uint32_t)g.img_bytes;
-  NK_CUDA_OK(cudaFuncSetAttribute(theta_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+  NK_CUDA_OK(cudaFuncSetAttribute(theta_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
   const int64_t n_blocks = (B + 127) / 128;
   int64_t ctas = (int64_t)(num_sms() / g.nt) * g.nt;
   if (ctas > n_blocks * g.nt) ctas = n_blocks * g.nt;
-  theta_tc_kernel<false><<<(int)ctas, 128, g.smem_bytes, stream>>>(a);
-  NK_LAUNCH_OK();
-  return NK_OK;
-}
-
-// y[s] = sum_j (sigma_s V + v_b)_j dot[s, j] + sigma_s . v_a with the dot fused into the GEMM epilogue (fp32 tcgen05 shapes
-// only).  Returns 1 when the shape is not covered (the caller then runs the GEMM and the row dot separately).
-int theta_gemm_dot(cudaStream_t stream, const nk_rbm_t &v, const int8_t *sigma, int64_t B, const void *dot, double *y, double *y_sum,
-                   void *workspace) {
-  TcGeom g;
-  if (theta_dmma_supported(v) || !tc_geometry(v, &g) || workspace == nullptr) return 1;
-  if (y_sum) NK_CUDA_OK(cudaMemsetAsync(y_sum, 0, sizeof(double), stream));
-  if (B == 0) return NK_OK;
-  if (g.nt > 1) NK_CUDA_OK(cudaMemsetAsync(y, 0, sizeof(double) * (size_t)B, stream));
-  uint16_t *img = reinterpret_cast<uint16_t *>(workspace);
-  {
-    const int total = g.nt * g.NT * g.kpad;
-    theta_prep_kernel<<<(total + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const float *>(v.W), v.N, v.M, g.kpad, g.nt, g.NT, g.sbo,
-                                                               img);
-    NK_LAUNCH_OK();
-  }
-  TcArgs a{};
-  a.sigma = sigma;
-  a.img = img;
-  a.bias = reinterpret_cast<const float *>(v.b);
-  a.theta = nullptr;
-  a.B = B;
-  a.N = v.N;
-  a.M = v.M;
-  a.kpad = g.kpad;
-  a.nt = g.nt;
-  a.NT = g.NT;
-  a.sbo = g.sbo;
-  a.tmem_cols = g.tmem_cols;
-  a.acc_cols = g.acc_cols;
-  // 128-bit loads of dot[row, tile chunk]: rows, tiles (NT) and chunks (multiples of 16 columns) must stay 16-byte aligned
-  a.vec_ok = (v.M % 4 == 0) && (g.NT % 4 == 0) && ((reinterpret_cast<uintptr_t>(dot) & 15) == 0);
-  a.part_bytes = (uint32_t)g.part_bytes;
-  a.img_bytes = (uint32_t)g.img_bytes;
-  a.dot = reinterpret_cast<const float *>(dot);
-  a.va = reinterpret_cast<const float *>(v.a);
-  a.y = y;
-  a.y_sum = y_sum;
-  NK_CUDA_OK(cudaFuncSetAttribute(theta_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-  const int64_t n_blocks = (B + 127) / 128;
-  int64_t ctas = (int64_t)(num_sms() / g.nt) * g.nt;
-  if (ctas > n_blocks * g.nt) ctas = n_blocks * g.nt;
-  theta_tc_kernel<true><<<(int)ctas, 128, g.smem_bytes, stream>>>(a);
+  theta_tc_kernel<<<(int)ctas, 128, g.smem_bytes, stream>>>(a);
   NK_LAUNCH_OK();
   return NK_OK;
 }

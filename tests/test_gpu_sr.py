@@ -144,11 +144,11 @@ def test_driver_api(cuda):
 
 
 @pytest.mark.parametrize("N,M,B,dtype,biases", [
-    (10, 20, 300, np.float32, (True, True)),      # tcgen05 with the dot fused into the epilogue, one column tile, 128-bit loads
-    (20, 320, 1000, np.float32, (True, True)),    # two column tiles (two CTAs add into y[row])
-    (100, 400, 4096, np.float32, (True, True)),   # cfg-3 shape: the second tile ends in a 16-column chunk beyond M
+    (10, 20, 300, np.float32, (True, True)),      # tcgen05 GEMM, one column tile
+    (20, 320, 1000, np.float32, (True, True)),    # two column tiles
+    (100, 400, 4096, np.float32, (True, True)),   # cfg-3 shape
     (33, 52, 257, np.float32, (False, True)),     # odd N, no hidden bias
-    (16, 18, 130, np.float32, (True, False)),     # M % 4 != 0: scalar loads; no visible bias
+    (16, 18, 130, np.float32, (True, False)),     # M % 4 != 0: scalar stores; no visible bias
     (6, 12, 200, np.float32, (True, True)),       # M < 16: GEMM on CUDA cores + separate row dot
     (20, 40, 500, np.float64, (True, True)),      # fp64: DMMA GEMM + separate row dot
 ])
