@@ -159,3 +159,57 @@ def test_cfg2_heisenberg1d(cuda):
     ref = oest.local_estimators(samples, lambda x: oops.local_operator_conn_padded(x, tables), W, b, a)
     np.testing.assert_allclose(vs.local_estimators(op).cpu().numpy(), ref, rtol=1e-10, atol=1e-10 * np.abs(ref).max())
     np.testing.assert_allclose(st.mean, ref.mean(), rtol=1e-10)
+
+
+def test_cfg3_streaming_statistics_full_size(cuda):
+    """2^16 chains x 16 local energies per batch (cfg-3's E_loc shape): size-independent properties of the accumulator.
+    Feeding a batch in four pieces equals feeding it at once; mean / variance equal the float64 moments of all samples
+    (torch reference, 1e-12); split chains give the same pooled moments; the ACF starts at 1."""
+    from netket_b200 import stats as nkstats
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn((2 ** 16, 16), dtype=torch.float64, device=cuda, generator=g).cumsum(dim=1) * 0.3 - 300.0
+    y = torch.randn((2 ** 16, 16), dtype=torch.float64, device=cuda, generator=g) * 0.5 - 300.0
+    one = nkstats.online_statistics(y, nkstats.online_statistics(x, max_lag=64))
+    pieces = None
+    for part in (x[:, :3], x[:, 3:4], x[:, 4:16], y[:, :9], y[:, 9:]):
+        pieces = nkstats.online_statistics(part.contiguous(), pieces, max_lag=64)
+    for f in ("_chain_count", "_chain_mean", "_chain_M2", "_cross_sum", "_m1_sum", "_m2_sum", "_pair_count", "_chain_buf"):
+        torch.testing.assert_close(getattr(pieces, f), getattr(one, f), rtol=1e-11, atol=1e-9, msg=f)
+    allx = torch.cat([x, y], dim=1)
+    np.testing.assert_allclose(one.mean, allx.mean().item(), rtol=1e-13)
+    np.testing.assert_allclose(one.variance, allx.var(unbiased=False).item(), rtol=1e-10)
+    assert one.n_samples == 2 ** 21 and one.acf[0] == 1.0 and one.acf.shape == (65,)
+    assert float(one._pair_count[0, 0]) == 32.0 and float(one._pair_count[7, 31]) == 1.0 and float(one._pair_count[7, 32]) == 0.0
+    np.testing.assert_allclose(one.error_of_mean, (allx.mean(dim=1).var(unbiased=False) / 2 ** 16).sqrt().item(), rtol=1e-10)
+    # float32 input: same state up to the rounding of the data
+    one32 = nkstats.online_statistics(y.float(), nkstats.online_statistics(x.float(), max_lag=64))
+    np.testing.assert_allclose(one32.mean, one.mean, rtol=1e-7)
+    np.testing.assert_allclose(one32.variance, one.variance, rtol=1e-3)
+
+
+def test_cfg3_qgt_full_size_properties(cuda):
+    """The matrix-free S on cfg-3 (2^18 samples here, 40 500 parameters): symmetric (u.Sv == v.Su), positive (v.Sv >= shift |v|^2),
+    linear, and constant shifts of log psi do not matter (S annihilates nothing but its shift on the all-equal direction of O)."""
+    nk = _nk()
+    from netket_b200.optimizer import QGTOnTheFly
+
+    g = nk.graph.Hypercube(10, 2)
+    hi = nk.hilbert.Spin(0.5, 100)
+    H = nk.operator.Ising(hi, g, h=3.0)
+    for dtype, tol in ((np.float32, 2e-4), (np.float64, 1e-10)):
+        vs = nk.vqs.MCState(nk.sampler.MetropolisLocal(hi, n_chains=2 ** 14), nk.models.RBM(alpha=4, param_dtype=dtype), n_samples=2 ** 18,
+                            seed=3)
+        vs.expect_and_grad(H)
+        S = QGTOnTheFly(vs, diag_shift=0.01)
+        n = S.shape[0]
+        gen = torch.Generator(device="cuda").manual_seed(1)
+        u = torch.randn(n, dtype=torch.float64, device=cuda, generator=gen)
+        v = torch.randn(n, dtype=torch.float64, device=cuda, generator=gen)
+        Su, Sv = S @ u, S @ v
+        a, b = torch.dot(u, Sv).item(), torch.dot(v, Su).item()
+        assert abs(a - b) <= tol * max(abs(a), abs(b), torch.dot(v, Sv).item())
+        assert torch.dot(v, Sv).item() >= 0.01 * torch.dot(v, v).item() * (1 - 1e-6)
+        lin = S @ (2.0 * u - 3.0 * v)
+        ref = 2.0 * Su - 3.0 * Sv
+        assert (lin - ref).abs().max().item() <= tol * ref.abs().max().item() * 10
