@@ -4,11 +4,13 @@ driver calls as the reference script (SGD with the SR preconditioner, netket/dri
     python examples/ising1d.py [n_iter]
 """
 
+import os
 import sys
 
 import torch
 
-import netket_b200 as nk
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import netket_b200 as nk  # noqa: E402
 
 L = 20
 g = nk.graph.Hypercube(length=L, n_dim=1, pbc=True)
