@@ -34,6 +34,25 @@ for dtype in (np.float64, np.float32):
         # chains are distinct across ranks (global chain index keys the stream)
         distinct = len({S[i * B].tobytes() for i in range(ws)}) == ws
         print(f"dist_check {np.dtype(dtype).name} ws={ws}: stats+grad {'OK' if ok else 'MISMATCH'}, distinct shards {distinct}, E = {st}")
+    # matrix-free QGT: every rank contracts its own samples, 1 + n_parameters doubles are all-reduced per product
+    from netket_b200.optimizer import QGTOnTheFly, SR, tree_to_flat
+    vs.reset(); st, G = vs.expect_and_grad(op)
+    Sq = QGTOnTheFly(vs, diag_shift=0.01)
+    vvec = torch.from_numpy(np.random.default_rng(11).normal(size=Sq.shape[0])).cuda()
+    got_sv = (Sq @ vvec).cpu().numpy()
+    dp = tree_to_flat(SR(diag_shift=0.01)(vs, G)).cpu().numpy()
+    samples = [torch.empty_like(vs.samples) for _ in range(ws)]; dist.all_gather(samples, vs.samples)
+    if rank == 0:
+        from oracle import qgt as oqgt
+        S_all = torch.cat(samples).cpu().numpy()
+        W = var["params"]["Dense"]["kernel"].cpu().numpy().astype(np.float64); b = var["params"]["Dense"]["bias"].cpu().numpy().astype(np.float64)
+        a = var["params"]["visible_bias"].cpu().numpy().astype(np.float64)
+        want_sv = oqgt.mat_vec(S_all, W, b, a, vvec.cpu().numpy(), 0.01)
+        want_dp = oqgt.sr_solve(S_all, W, b, a, tree_to_flat(G).cpu().numpy(), 0.01)
+        tol = 1e-10 if dtype == np.float64 else 3e-5
+        ok = np.abs(got_sv - want_sv).max() <= tol * np.abs(want_sv).max() and np.abs(dp - want_dp).max() <= 2e-3 * np.abs(want_dp).max()
+        print(f"dist_check {np.dtype(dtype).name} ws={ws}: QGT product + SR solve over {S_all.shape[0] * S_all.shape[1]} samples {'OK' if ok else 'MISMATCH'} "
+              f"(product err {np.abs(got_sv - want_sv).max() / np.abs(want_sv).max():.1e}, solve err {np.abs(dp - want_dp).max() / np.abs(want_dp).max():.1e})")
     # streaming statistics: every rank accumulates its own chains, the derived quantities all-reduce the summary sums
     from netket_b200.stats import online_statistics
     acc = None
