@@ -278,7 +278,10 @@ __global__ void __launch_bounds__(FAST_THREADS, 1)
   int lane_o = lane;
   asm volatile("" : "+r"(rc_s), "+r"(lane_row), "+r"(lane_tail), "+r"(sweep_size), "+r"(lane_o));
 
-  for (int chain = blockIdx.x * FAST_WARPS + warp; chain < (int)p.B; chain += gridDim.x * FAST_WARPS) {
+  // chains are dealt out warp-major (round r gives warp w of CTA b the chain (r * FAST_WARPS + w) * gridDim + b): the chains of
+  // the last, partial round (2^16 chains = 15.8 rounds of 148 x 28 warps) then thin out every SM equally instead of leaving
+  // whole SMs idle while the others run a full round
+  for (int chain = warp * gridDim.x + blockIdx.x; chain < (int)p.B; chain += gridDim.x * FAST_WARPS) {
     ChainRegs<NP> c;
     // ---- sigma, lane-distributed: lane l keeps the bits of sites l, 32 + l, 64 + l, 96 + l
     c.mybits = 0;
