@@ -120,3 +120,82 @@ def test_stopping_tests_of_expect_to_precision():
         conv.expect_to_precision(NotMetropolis(), None)
     with pytest.raises(ValueError, match="rtol must be > 0"):
         conv.expect_to_precision(NotMetropolis(), None, rtol=0.0)
+
+
+class QuadraticState:
+    """A stand-in variational state whose 'energy' is |p - target|^2 / 2 (gradient p - target): the driver's loop logic
+    (netket/driver/vmc.py:141-161, abstract_variational_driver.py:349-528) runs on CPU tensors."""
+
+    hilbert = "hi"
+    n_samples, n_parameters = 100, 8
+
+    def __init__(self):
+        self.parameters = {"Dense": {"kernel": torch.zeros(2, 3, dtype=torch.float64)}, "visible_bias": torch.zeros(2, dtype=torch.float64)}
+        self.target = {"Dense": {"kernel": torch.full((2, 3), 2.0, dtype=torch.float64)}, "visible_bias": torch.full((2,), -1.0, dtype=torch.float64)}
+        self.resets = 0
+
+    def reset(self):
+        self.resets += 1
+
+    def _loss(self):
+        d = opt.tree_to_flat(self.parameters) - opt.tree_to_flat(self.target)
+        return 0.5 * float(d @ d)
+
+    def expect_and_grad(self, op):
+        from netket_b200.stats import Stats
+
+        g = opt._tree_map2(lambda p, t: p - t, self.parameters, self.target)
+        return Stats(mean=self._loss(), error_of_mean=0.0, variance=0.0), g
+
+    def expect(self, op):
+        from netket_b200.stats import Stats
+
+        return Stats(mean=self._loss())
+
+
+class Op:
+    hilbert = "hi"
+
+
+def test_vmc_driver_loop_on_cpu():
+    vs = QuadraticState()
+    d = drv.VMC(Op(), opt.Sgd(0.5), variational_state=vs)
+    log = drv.RuntimeLog()
+    d.run(20, out=log, obs={"again": Op()}, show_progress=False)
+    assert d.step_count == 20 and vs.resets >= 20
+    e = log["Energy"]["Mean"]
+    assert e.iters == list(range(20)) and all(b < a for a, b in zip(e.values, e.values[1:])) and e.values[-1] < 1e-9
+    assert len(log["again"]["Mean"]) == 20
+    assert torch.allclose(vs.parameters["visible_bias"], torch.full((2,), -1.0, dtype=torch.float64), atol=1e-5)
+    # iter(): yields the step count every `step` steps; advance(); callbacks stop the run; step_size thins the log
+    assert list(d.iter(6, 3)) == [20, 23] and d.step_count == 26
+    d.advance(4)
+    assert d.step_count == 30
+    seen = []
+    d.run(10, show_progress=False, callback=[lambda s, l, drv_: True, lambda s, l, drv_: (seen.append(s) or len(seen) < 2)])
+    assert seen == [30, 31]
+    log2 = drv.RuntimeLog()
+    d.run(6, out=log2, step_size=2, show_progress=False)
+    assert len(log2["Energy"]["Mean"]) == 3
+    d.reset()
+    assert d.step_count == 0
+    # a preconditioner is called as (state, grad, step); None means identity
+    calls = []
+
+    def halve(state, grad, step=None):
+        calls.append(step)
+        return opt._tree_map(lambda g: 0.5 * g, grad)
+
+    d2 = drv.VMC(Op(), opt.Sgd(1.0), variational_state=QuadraticState(), preconditioner=halve)
+    d2.advance(3)
+    assert calls == [0, 1, 2] and abs(d2.state.parameters["visible_bias"][0].item() + 1.0 * (1 - 0.5 ** 3)) < 1e-12
+    d2.preconditioner = None
+    assert d2.preconditioner is opt.identity_preconditioner
+
+    class Other:
+        hilbert = "other"
+
+    with pytest.raises(TypeError, match="should match"):
+        drv.VMC(Other(), opt.Sgd(0.1), variational_state=vs)
+    with pytest.raises(ValueError, match="must be a number"):
+        d.run("ten")
