@@ -232,6 +232,8 @@ int online_stats_finalize(const double *p0, const double *p1, int64_t n_chains, 
   for (int i = 0; i < NK_ONLINE_NOUT; ++i) o[i] = nan;
   o[7] = 0.0;
   o[8] = 0.0;
+  if (acf)
+    for (int k = 0; k <= L && L > 0; ++k) acf[k] = nan;  // NaN = no autocorrelation function (accumulator.py:353-377 returns None)
   const double total = p0[0];
   if (total == 0.0) return NK_OK;
   const double nc = (double)n_chains;

@@ -272,8 +272,9 @@ def online_finalize(p0, p1, n_chains, n_samples, max_lag):
     acf = (C.c_double * max(n_lag, 1))()
     _lib.check(_lib.lib().nk_online_stats_finalize(a0, a1, max(int(n_chains), 1), int(n_samples), int(max_lag), out, acf))
     acf = np.array(acf[:n_lag])
-    return dict(out=list(out), acf=None if n_lag == 0 or np.isnan(acf[0]) else acf, n_chains=int(n_chains), n_samples=int(n_samples),
-                empty=float(p0[0]) == 0.0)
+    empty = float(p0[0]) == 0.0
+    return dict(out=list(out), acf=None if n_lag == 0 or empty or np.isnan(acf[0]) else acf, n_chains=int(n_chains), n_samples=int(n_samples),
+                empty=empty)
 
 
 def _as_device_2d(data):

@@ -138,3 +138,23 @@ def test_oracle_errors_and_empty():
         oos.expand_max_lag(e, 4)
     with pytest.raises(ValueError, match="thin"):
         oos.thin_acf_by_2(oos.OnlineStats(3, max_lag=1))
+
+
+def test_host_finalize_edge_cases(lib_built):
+    """Empty accumulator (all NaN, as OnlineStats().get_stats() -> Stats()), a constant series (no ACF: cov[0] = 0), one sample
+    per chain, and the argument checks of the host entry point."""
+    from netket_b200 import stats as nkstats
+
+    s = nkstats.online_finalize([0.0, 0.0, 0.0], [0.0] * (4 + 9), 4, 0, 8)
+    assert s["empty"] and all(math.isnan(v) for v in s["out"][:7]) and s["out"][7:] == [0.0, 0.0] and s["acf"] is None
+    const = oos.online_statistics(np.full((3, 20), 2.5), max_lag=4)
+    got = finalize_from_oracle_state(const)
+    assert got["acf"] is None and const.acf is None and math.isnan(got["out"][6]) and got["out"][0] == 2.5 and got["out"][2] == 0.0
+    assert math.isnan(got["out"][4]) and math.isnan(const.R_hat)              # W = 0: no R_hat
+    assert math.isnan(got["out"][5]) and math.isnan(const.tau_corr_batch)     # variance = 0: no batch tau
+    one = oos.online_statistics(np.random.default_rng(0).normal(size=(6, 1)), max_lag=4)
+    got = finalize_from_oracle_state(one)
+    want = [one.mean, one.error_of_mean, one.variance, one.tau_corr, one.R_hat, one.tau_corr_batch, one.tau_corr_acf]
+    np.testing.assert_allclose(got["out"][:7], want, rtol=1e-12, equal_nan=True)
+    with pytest.raises(Exception, match="bad arguments"):
+        nkstats.online_finalize([1.0, 1.0, 1.0], [0.0] * 4, 4, 4, 5000)
