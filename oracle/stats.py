@@ -52,3 +52,46 @@ def statistics(data, batch_size=32):
     else:
         R_hat = np.nan
     return dict(mean=mean, error_of_mean=error_of_mean, variance=variance, tau_corr=tau_corr, R_hat=R_hat)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# FFT variant (opt-in in the reference: flag NETKET_EXPERIMENTAL_FFT_AUTOCORRELATION; netket/stats/mc_stats.py:303-331,
+# netket/stats/_autocorr.py:32-86).  Pinned by tests/golden/online_stats_vectors.npz (keys fft_*).  No product code yet.
+# ------------------------------------------------------------------------------------------------------------------
+def autocorr_1d(x):
+    """Normalised autocorrelation function of one series; the direct O(L^2) sum the zero-padded FFT evaluates."""
+    x = np.asarray(x, dtype=np.float64)
+    d = x - x.mean()
+    L = d.size
+    acf = np.array([np.dot(d[: L - k], d[k:]) for k in range(L)])
+    return acf / acf[0]
+
+
+def integrated_time(x, c=5):
+    """Sokal's automatic window: tau(M) = 2 sum_{k<=M} rho_k - 1 at the first M with M >= c tau(M).  As the reference codes it
+    (`auto_window`, _autocorr.py:62-64): `argmin(M < c tau)`, which is 0 when no M qualifies, and the last M when every M does."""
+    taus = 2.0 * np.cumsum(autocorr_1d(x)) - 1.0
+    m = np.arange(taus.size) < c * taus
+    window = int(np.argmin(m)) if m.any() else taus.size - 1
+    return taus[window]
+
+
+def statistics_fft(data):
+    data = np.atleast_1d(np.asarray(data, dtype=np.float64))
+    if data.ndim == 1:
+        data = data.reshape(1, -1)
+    n_chains, L = data.shape
+    mean, variance = data.mean(), data.var()
+    taus = np.array([integrated_time(row) for row in data])
+    if n_chains > 1:
+        error_of_mean = np.sqrt(data.mean(axis=1).var() / n_chains)
+        half = data if L % 2 == 0 else data[:, :-1]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            R_hat = np.sqrt((L - 1) / L + half.reshape(2 * n_chains, L // 2).mean(axis=1).var() / variance)
+    else:
+        l_block = max(1, L // 32)
+        n_b = L // l_block
+        blocks = data[:, : n_b * l_block].reshape(-1, l_block).mean(axis=1)
+        error_of_mean = np.sqrt(blocks.var() / blocks.size)
+        R_hat = np.nan
+    return dict(mean=mean, error_of_mean=error_of_mean, variance=variance, tau_corr=taus.mean(), R_hat=R_hat, tau_corr_max=taus.max())

@@ -77,11 +77,15 @@ def _make_jnp():
     jnp = types.ModuleType("jax.numpy")
     for name in ("zeros", "ones", "full", "arange", "eye", "asarray", "array", "abs", "exp", "log", "log1p", "sqrt", "sum", "mean",
                  "var", "hstack", "broadcast_to", "expand_dims", "take", "signbit", "atleast_1d", "swapaxes", "dot",
-                 "isclose", "concatenate", "stack", "max", "min", "floor", "zeros_like", "pad", "real", "minimum", "maximum", "all"):
+                 "isclose", "concatenate", "stack", "max", "min", "floor", "zeros_like", "pad", "real", "minimum", "maximum", "all", "cumsum", "argmin", "any", "conjugate"):
         setattr(jnp, name, _lift(getattr(np, name)))
     jnp.where = _where
     jnp.clip = lambda a, min=None, max=None: _wrap(np.clip(a, min, max))  # noqa: A002  (jnp.clip(x, 0) == lower bound only)
     jnp.nan = np.nan
+    fft = types.ModuleType("jax.numpy.fft")
+    fft.fft = _lift(np.fft.fft)
+    fft.ifft = _lift(np.fft.ifft)
+    jnp.fft = fft
     jnp.inf = np.inf
     jnp.int32, jnp.int64, jnp.float32, jnp.float64, jnp.bool_ = np.int32, np.int64, np.float32, np.float64, np.bool_
     jnp.bool = np.bool_

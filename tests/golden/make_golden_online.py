@@ -136,6 +136,22 @@ for tag, nc, L, decay, lens, phi, dt in CASES:
         dump(out, f"{tag}_after", x.update(more))
 out["cases"] = np.array(cases)
 
+# ------------------------------------------------------------------ FFT statistics (netket/stats/mc_stats.py:303-331, _autocorr.py:32-86)
+import types  # noqa: E402
+
+ns_a = extract("stats/_autocorr.py", ["next_pow_two", "autocorr_1d", "auto_window", "integrated_time"], {**base_ns(), "lax": lax})
+FftStats = lambda *a: a  # noqa: E731
+ns_f = extract("stats/mc_stats.py", ["_get_blocks", "_block_variance", "_batch_variance", "_split_R_hat", "_statistics"],
+               {**base_ns(), "Stats": FftStats, "config": types.SimpleNamespace(netket_use_plain_rhat=False), "BLOCK_SIZE": 32,
+                "integrated_time": ns_a["integrated_time"]})
+for tag, shape, phi in [("fft_16x200", (16, 200), 0.7), ("fft_1x500", (1, 500), 0.5), ("fft_8x33", (8, 33), 0.2), ("fft_3x7", (3, 7), 0.9)]:
+    data = ar1(rs, shape[0], shape[1], phi)
+    res = ns_f["_statistics"](jnp.asarray(data))
+    out[f"{tag}_data"] = data
+    out[f"{tag}_result"] = np.array([float(np.asarray(v)) for v in res])     # mean, error, variance, tau_avg, R_hat, tau_max
+    out[f"{tag}_acf0"] = np.asarray(ns_a["autocorr_1d"](jnp.asarray(data[0])))
+out["fft_cases"] = np.array(["fft_16x200", "fft_1x500", "fft_8x33", "fft_3x7"])
+
 path = os.path.join(HERE, "online_stats_vectors.npz")
 np.savez_compressed(path, **out)
 print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path) / 1024:.1f} KiB")

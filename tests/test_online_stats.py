@@ -158,3 +158,15 @@ def test_host_finalize_edge_cases(lib_built):
     np.testing.assert_allclose(got["out"][:7], want, rtol=1e-12, equal_nan=True)
     with pytest.raises(Exception, match="bad arguments"):
         nkstats.online_finalize([1.0, 1.0, 1.0], [0.0] * 4, 4, 4, 5000)
+
+
+@pytest.mark.parametrize("tag", [str(t) for t in GOLD["fft_cases"]])
+def test_fft_statistics_oracle_matches_reference_vectors(tag):
+    """The opt-in FFT variant of `statistics` (mc_stats.py:303-331, _autocorr.py:32-86): oracle only so far."""
+    from oracle import stats as ostats
+
+    data = GOLD[f"{tag}_data"]
+    np.testing.assert_allclose(ostats.autocorr_1d(data[0]), GOLD[f"{tag}_acf0"], rtol=1e-9, atol=1e-12)
+    r = ostats.statistics_fft(data)
+    got = [r["mean"], r["error_of_mean"], r["variance"], r["tau_corr"], r["R_hat"], r["tau_corr_max"]]
+    np.testing.assert_allclose(got, GOLD[f"{tag}_result"], rtol=1e-9, atol=1e-12, equal_nan=True)
