@@ -39,7 +39,7 @@ extern "C" {
 #define NK_EUNSUPPORTED (-3)
 
 #define NK_RULE_LOCAL 0    /* netket/sampler/rules/local.py:23-52 */
-#define NK_RULE_EXCHANGE 1 /* netket/sampler/rules/exchange.py:25-187, probabilities=None */
+#define NK_RULE_EXCHANGE 1 /* netket/sampler/rules/exchange.py:25-187 (nk_sweep_t.cluster_probs: probabilities=) */
 
 /* kernel-path selection for the sweep / E_loc kernels (NK_PATH_AUTO picks the fastest valid one) */
 #define NK_PATH_AUTO 0
@@ -128,6 +128,18 @@ typedef struct nk_sweep_t {
   /* optional: tanh(theta) of every recorded sample, [B, chain_length, M] in the rbm dtype.  The sweep kernels hold it in
    * registers anyway ((A - B) / (A + B)); nk_forces_rbm takes it instead of recomputing theta for the whole batch */
   void *tanh_out;
+  /* optional: MC statistics of the fused local energies, reduced inside the sweep kernel (netket/stats/mc_stats_old.py:87-196).
+   * stats_out: NK_STATS_NPARTIAL doubles (device, zeroed by the call) that receive the phase-1 sums of nk_stats_partial
+   * over this launch's eloc_out [B, chain_length] with shift = stats_shift (any estimate of the mean: the previous step's
+   * energy; the sums are exact in real arithmetic for every shift, accumulated in double).  The caller all-reduces them over
+   * GPUs and calls nk_stats_finalize(sums, stats_shift, ...); nk_stats_finalize returns mean = stats_shift + sums[7] / n. */
+  double *stats_out;
+  double stats_shift;
+  /* ExchangeRule(probabilities=...) (netket/sampler/rules/exchange.py:86-123,155-160,177-182): relative weight of every
+   * cluster, [n_clusters] doubles > 0 (device), or NULL for the uniform rule.  The cluster is drawn with weight
+   * hoppable * p by inverse CDF in cluster order (jax.random.choice's algorithm) at r = (w0 + 1/2) / 2^32, and the
+   * log-ratio correction is log sum_c w_c(sigma) - log sum_c w_c(sigma'). */
+  const double *cluster_probs;
 } nk_sweep_t;
 
 const char *nk_last_error(void);
@@ -182,8 +194,10 @@ int nk_eloc_localop_rbm(void *stream, const nk_rbm_t *rbm, const nk_localop_t *o
 #define NK_STATS_NPARTIAL 8
 int nk_stats_partial(void *stream, const void *data, int32_t dtype, int64_t n_chains, int64_t L, int32_t phase, double shift,
                      double *partials_out);
-/* host-only arithmetic: sums_host = all-reduced phase-1 partials; out_host = {mean, error_of_mean, variance, tau_corr, R_hat} */
-int nk_stats_finalize(const double *sums_host, double mean, int64_t n_chains_total, int64_t L, double *out_host);
+/* host-only arithmetic: sums_host = all-reduced phase-1 partials, shift = the `shift` they were taken around (the mean of
+ * phase 0, or any estimate for the one-pass reduction of nk_sweep_t.stats_out): mean = shift + sums[7] / n.
+ * out_host = {mean, error_of_mean, variance, tau_corr, R_hat} */
+int nk_stats_finalize(const double *sums_host, double shift, int64_t n_chains_total, int64_t L, double *out_host);
 
 /* Streaming statistics: OnlineStats (netket/_src/stats/online_stats/accumulator.py:31-447), the accumulator behind
  * thermalise_mcmc / check_mc_convergence / expect_to_precision (netket/_src/vqs/check_mc_convergence.py,

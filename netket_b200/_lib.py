@@ -61,7 +61,8 @@ class nk_sweep_t(C.Structure):
                 ("machine_pow", C.c_double), ("samples_out", C.c_void_p), ("logp_out", C.c_void_p),
                 ("stream_w0", C.c_void_p), ("stream_u", C.c_void_p), ("clusters", C.c_void_p), ("n_clusters", C.c_int32),
                 ("path", C.c_int32), ("ising", C.POINTER(nk_ising_t)), ("localop", C.POINTER(nk_localop_t)),
-                ("eloc_out", C.c_void_p), ("eloc_dtype", C.c_int32), ("reserved", C.c_int32), ("tanh_out", C.c_void_p)]
+                ("eloc_out", C.c_void_p), ("eloc_dtype", C.c_int32), ("reserved", C.c_int32), ("tanh_out", C.c_void_p),
+                ("stats_out", C.c_void_p), ("stats_shift", C.c_double), ("cluster_probs", C.c_void_p)]
 
 
 # every symbol include/nkb200.h declares: name -> (restype, argtypes)

@@ -47,7 +47,7 @@ int ising_n_conn(cudaStream_t stream, const nk_ising_t &op, const int8_t *x, int
 int localop_conn(cudaStream_t stream, const nk_localop_t &op, const int8_t *x, int64_t B, int32_t N, int8_t *xp, void *mels,
                  int32_t mel_dtype, int32_t *nconn);
 int stats_partial(cudaStream_t stream, const void *data, int32_t dtype, int64_t n_chains, int64_t L, int32_t phase, double shift,
-                  double *out);
+                  double *out, const int *run_if = nullptr);
 int stats_finalize(const double *p, double mean, int64_t n_chains, int64_t L, double *out);
 int rbm_tanh_inplace(cudaStream_t stream, void *x, int32_t dtype, int64_t n);
 int rbm_jvp_dot(cudaStream_t stream, const nk_rbm_t &v, const int8_t *sigma, int64_t Ns, const void *t, const void *g, double *y,
@@ -166,6 +166,8 @@ int nk_sweep(void *stream, const nk_rbm_t *rbm, nk_chains_t *ch, const nk_sweep_
     if (rc) return rc;
   }
   NK_CHECK_ARG(a->path >= NK_PATH_AUTO && a->path <= NK_PATH_PROD, "nk_sweep: bad path %d", a->path);
+  NK_CHECK_ARG(a->stats_out == nullptr || a->ising || a->localop, "nk_sweep: stats_out needs a fused operator (ising / localop)");
+  if (a->stats_out) NK_CUDA_OK(cudaMemsetAsync(a->stats_out, 0, sizeof(double) * NK_STATS_NPARTIAL, (cudaStream_t)stream));
   if (ch->B == 0) return NK_OK;
 
   SweepKernelArgs k{};
@@ -194,6 +196,10 @@ int nk_sweep(void *stream, const nk_rbm_t *rbm, nk_chains_t *ch, const nk_sweep_
   k.eloc_out = a->eloc_out;
   k.eloc_dtype = a->eloc_dtype;
   k.tanh_out = a->tanh_out;
+  k.stats_out = a->stats_out;
+  k.stats_shift = a->stats_shift;
+  k.cluster_probs = a->rule == NK_RULE_EXCHANGE ? a->cluster_probs : nullptr;
+  const int *stats_guard = nullptr;  // the tuned fp32 kernel reduces its energies itself; the other kernels leave it to K6
 
   // path selection: the tuned fp32 LocalRule kernel (sweep_fast) where it applies, the general product-form kernel
   // (sweep_prod: fp32/fp64, both rules, Ising / LocalOperator) otherwise, the theta-form generic kernel as the last resort
@@ -222,6 +228,7 @@ int nk_sweep(void *stream, const nk_rbm_t *rbm, nk_chains_t *ch, const nk_sweep_
       // tuned fp32 kernel first; if the weights are beyond its range (flags[0]) the general kernel's wide mode takes over
       // in-stream, and only if that gives up as well (flags[5]) the theta-form kernel runs
       rc = sweep_fast(st, k, reinterpret_cast<const float *>(theta), flags);
+      stats_guard = flags;  // flags[0] != 0: the tuned kernel handed over without producing anything
       if (rc == NK_OK && a->path != NK_PATH_FAST && sweep_prod_supported(k)) {
         rc = sweep_prod(st, k, theta, flags, tables, flags, 5);
         guard = flags + 5;
@@ -239,6 +246,9 @@ int nk_sweep(void *stream, const nk_rbm_t *rbm, nk_chains_t *ch, const nk_sweep_
   } else {
     rc = sweep_generic((cudaStream_t)stream, k);
   }
+  // kernels without the fused reduction (and the hand-over targets of the tuned one, guarded by its flag): one pass of K6
+  if (rc == NK_OK && a->stats_out != nullptr && a->chain_length > 0)
+    rc = stats_partial((cudaStream_t)stream, a->eloc_out, a->eloc_dtype, ch->B, a->chain_length, 1, a->stats_shift, a->stats_out, stats_guard);
   if (rc == NK_OK) ch->t += (uint64_t)(a->n_discard + a->chain_length) * (uint64_t)a->sweep_size;
   return rc;
 }

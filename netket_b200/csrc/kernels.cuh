@@ -32,6 +32,11 @@ struct SweepKernelArgs {
   const int *run_if_flag;  // generic kernel only: run iff NULL or *run_if_flag != 0 (fast-path hand-over)
   void *tanh_out;          // optional [B, chain_length, M]: tanh(theta) of every recorded sample
   int32_t eloc_only;       // sweep_prod only: no proposals, eloc_out[chain] = E_loc(sigma[chain]) (stand-alone local estimator)
+  // optional in-kernel statistics of the fused local energies (nk_sweep_t.stats_out): NK_STATS_NPARTIAL shifted sums of
+  // this launch's [B, chain_length] values, laid out like the phase-1 output of nk_stats_partial with mu = stats_shift
+  double *stats_out;
+  double stats_shift;
+  const double *cluster_probs;  // ExchangeRule(probabilities=): [n_clusters] weights, or NULL (uniform)
 };
 
 // sweep_generic.cu — theta-form path (any shape / dtype / rule)

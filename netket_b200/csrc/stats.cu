@@ -26,8 +26,9 @@ __device__ __forceinline__ double block_sum(double v, double *sh) {
 
 template <typename T>
 __global__ void __launch_bounds__(256) stats_partial_kernel(const T *__restrict__ data, int64_t n_chains, int64_t L, int phase,
-                                                            double mu, double *__restrict__ out) {
+                                                            double mu, double *__restrict__ out, const int *__restrict__ run_if) {
   __shared__ double sh[8];
+  if (run_if != nullptr && *run_if == 0) return;  // the sweep kernel in front of this one reduced its energies itself
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
   double acc[NK_STATS_NPARTIAL];
 #pragma unroll
@@ -88,18 +89,19 @@ __global__ void __launch_bounds__(256) stats_partial_kernel(const T *__restrict_
   }
 }
 
+// run_if != NULL: accumulate into `out` (not zeroed here) iff *run_if != 0 when the kernel starts (in-stream hand-over).
 int stats_partial(cudaStream_t stream, const void *data, int32_t dtype, int64_t n_chains, int64_t L, int32_t phase, double shift,
-                  double *out) {
-  NK_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(double) * NK_STATS_NPARTIAL, stream));
+                  double *out, const int *run_if) {
+  if (run_if == nullptr) NK_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(double) * NK_STATS_NPARTIAL, stream));
   if (n_chains == 0 || L == 0) return NK_OK;
   const int warps = 8;
   const int64_t need = (n_chains + warps - 1) / warps;
   const int64_t cap = (int64_t)num_sms() * 4;
   const int grid = (int)(need < cap ? need : cap);
   if (dtype == NK_F32)
-    stats_partial_kernel<float><<<grid, warps * 32, 0, stream>>>((const float *)data, n_chains, L, phase, shift, out);
+    stats_partial_kernel<float><<<grid, warps * 32, 0, stream>>>((const float *)data, n_chains, L, phase, shift, out, run_if);
   else
-    stats_partial_kernel<double><<<grid, warps * 32, 0, stream>>>((const double *)data, n_chains, L, phase, shift, out);
+    stats_partial_kernel<double><<<grid, warps * 32, 0, stream>>>((const double *)data, n_chains, L, phase, shift, out, run_if);
   NK_LAUNCH_OK();
   return NK_OK;
 }
@@ -134,7 +136,7 @@ int stats_finalize(const double *p, double mean, int64_t n_chains, int64_t L, do
     const double hv = (L / 2) > 0 ? p[6] / nh - (p[5] / nh) * (p[5] / nh) : nan;
     rhat = sqrt(((double)L - 1.0) / (double)L + hv / variance);
   }
-  out[0] = mean + 0.0;
+  out[0] = mean + dm;  // dm: rounding noise when the shift was the mean itself, the whole correction for a one-pass shift
   out[1] = err;
   out[2] = variance;
   out[3] = tau;

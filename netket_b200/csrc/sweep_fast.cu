@@ -1,8 +1,9 @@
 // Product-form fast path of the Metropolis sweep (fp32, LocalRule, weight table resident in shared memory),
-// optionally fused with the transverse-field-Ising local energy.
+// optionally fused with the transverse-field-Ising local energy and the MC statistics of those energies.
 //
 // Replaces the hot loop of netket/sampler/metropolis.py:427-462 (+ rules/local.py:40-49) and, when fused,
-// netket/vqs/mc/kernels.py:62-71 with netket/operator/_ising/jax.py:125-165.
+// netket/vqs/mc/kernels.py:62-71 with netket/operator/_ising/jax.py:125-165 and the sums of
+// netket/stats/mc_stats_old.py:87-196.
 //
 // Math ("exponential form").  Each hidden unit is carried as an unnormalised positive pair
 //     (A_j, B_j)  proportional to  (exp(theta_j), exp(-theta_j)),     cosh(theta_j) ~ (A_j + B_j) / 2,
@@ -11,12 +12,19 @@
 //     nu = -1:  cosh(theta'_j) ~ exp(2 W_ij) (A_j G_ij + B_j) / 2      accept:  A_j <- A_j G_ij
 // so  delta_i = 2 nu a_i + 2 sum_j W_ij + log prod_j (A_j + B_j G_ij | A_j G_ij + B_j) - log prod_j (A_j + B_j).
 // Per (proposal, hidden unit) that is one FFMA and one FMUL, no transcendental and - every term being positive -
-// no cancellation, however saturated the unit is; the accept costs one FMUL.  Two lg2 per lane per proposal turn the
-// lane products into a sum; (A, B) are renormalised to A + B = 1 every `renorm` proposals, a period chosen from
-// max|W| so that no lane product can leave the fp32 range.
-// One warp owns one chain for the whole call; lanes own hidden units (packed as float2 -> FFMA2/FMUL2);
-// W is brought in once per CTA by TMA bulk copies and turned into the G table in place.
+// no cancellation, however saturated the unit is; the accept costs one FMUL.  One lg2 per lane per proposal turns the
+// lane products into a fixed-point sum (REDUX); (A, B) are renormalised to A + B = 1 every `renorm` accepted moves, a
+// period chosen from max|W| so that no lane product can leave the fp32 range.
+// One warp owns one chain for the whole call; lanes own hidden units (packed as float2 -> FFMA2/FMUL2, an odd unit as a
+// scalar); W is brought in once per CTA by TMA bulk copies and turned into the G table in place.
 // The binding resource is the shared-memory read of one G row (M floats) per proposal per chain.
+//
+// Proposal loop (v7).  The 32 proposals of a batch are prepared by the 32 lanes in parallel (Philox, site, threshold,
+// per-site constants) and left in a per-warp shared-memory record {row address, spin address, threshold - fix(x_i),
+// fix(y_i)}; a proposal then starts with ONE broadcast LDS.128 instead of three shuffles, the chain's spins live as
+// bytes in shared memory (one LDS.U8 to read, one STS.U8 on accept) and the whole accept test is integer:
+//   fix(log2 ratio) = (Rp - R) + fix(x_i) +- fix(y_i),   x_i = log2e 2 sum_j W_ij,  y_i = log2e 2 a_i,
+//   accept = u < exp(machine_pow * delta)  <=>  fix(log2(u) / machine_pow) < fix(log2 ratio)   (metropolis.py:444-450).
 //
 // Validity: 2 NP * (4 max|W| log2 e) <= 120 (|W| <~ 1.5 at 14 units per lane); otherwise the kernel raises a device flag and
 // the kernels enqueued behind it do the work without a host round trip: the general product-form kernel in its wide mode
@@ -38,7 +46,11 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<u64 *>(&a)), "l"(*reinterpret_cast<u64 *>(&b)));
   return *reinterpret_cast<float2 *>(&d);
 }
-__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  u64 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<u64 *>(&a)), "l"(*reinterpret_cast<u64 *>(&b)));
+  return *reinterpret_cast<float2 *>(&d);
+}
 
 // ---- mbarrier / TMA bulk copy (global -> shared), PTX
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -68,22 +80,30 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
                : "memory");
 }
 
-#ifndef NK_FAST_PREFETCH
-#define NK_FAST_PREFETCH 0
-#endif
 #ifndef NK_FAST_WARPS
 #define NK_FAST_WARPS 28
 #endif
 constexpr int FAST_WARPS = NK_FAST_WARPS;
 constexpr int FAST_THREADS = FAST_WARPS * 32;
-constexpr float EXP_RANGE = 120.0f;  // log2 headroom allowed for a lane product
-constexpr float FX_SCALE = 524288.0f;            // 2^19: fixed-point scale of per-lane log2 partials (REDUX add)
+constexpr float EXP_RANGE = 120.0f;      // log2 headroom allowed for a lane product
+constexpr float FX_SCALE = 524288.0f;    // 2^19: fixed-point scale of per-lane log2 partials (REDUX add)
+constexpr int THR_MIN = -(1 << 29);      // "always accept" threshold (u == 0 or machine_pow == 0): -1024 in log2 units
+constexpr int SIG_STRIDE = 128;          // spin bytes per warp (N <= 128)
+constexpr int WSTAT = 12;                // doubles of statistics scratch per warp
 
 // ---- explicit shared-space accesses (32-bit shared addresses kept in registers; no generic-address arithmetic)
 __device__ __forceinline__ float4 lds128(uint32_t a) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
   return v;
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128u(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ float2 lds64(uint32_t a) {
   float2 v;
@@ -95,6 +115,12 @@ __device__ __forceinline__ float lds32(uint32_t a) {
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
   return v;
 }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ float lg2_fast(float x) {  // x is a positive normal number by construction
   float y;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -105,33 +131,44 @@ __device__ __forceinline__ float ex2_fast(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float rcp_fast(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
+// A lane owns NE = 4 NFULL + TAIL hidden units: NP2 float2 pairs (FFMA2 / FMUL2) plus, for TAIL == 1, one scalar.
 template <int NFULL, int TAIL>
 struct Lanes {
-  static constexpr int NE = 4 * NFULL + TAIL;        // hidden units per lane
-  static constexpr int NP = (NE + 1) / 2;            // float2 pairs per lane
-  static constexpr int MP = 128 * NFULL + 32 * TAIL; // padded row length of the G table (floats)
+  static constexpr int NE = 4 * NFULL + TAIL;                      // hidden units per lane
+  static constexpr int NP2 = 2 * NFULL + (TAIL == 2 ? 1 : 0);      // float2 pairs per lane
+  static constexpr int NPA = NP2 > 0 ? NP2 : 1;                    // array extent (no zero-sized arrays)
+  static constexpr bool HAS_T = TAIL == 1;                         // odd unit carried as a scalar
+  static constexpr int MP = 128 * NFULL + 32 * TAIL;               // padded row length of the G table (floats)
   // hidden-unit index of element e of this lane (may be >= M: padding)
   static __device__ __forceinline__ int unit(int e, int lane) {
     return e < 4 * NFULL ? 128 * (e >> 2) + 4 * lane + (e & 3) : 128 * NFULL + TAIL * lane + (e - 4 * NFULL);
   }
   // row_lane = shared address of G[i][0] + 16 * lane ; tail_lane = shared address of G[i][128*NFULL + TAIL*lane]
-  static __device__ __forceinline__ void load_row(uint32_t row_lane, uint32_t tail_lane, float2 (&g2)[NP]) {
+  static __device__ __forceinline__ void load_row(uint32_t row_lane, uint32_t tail_lane, float2 (&g2)[NPA], float &gt) {
 #pragma unroll
     for (int q = 0; q < NFULL; ++q) {
       const float4 v = lds128(row_lane + 512 * q);
       g2[2 * q] = make_float2(v.x, v.y);
       g2[2 * q + 1] = make_float2(v.z, v.w);
     }
-    if (TAIL == 1) g2[2 * NFULL] = make_float2(lds32(tail_lane), 1.0f);  // odd element count: neutral partner (G = 1)
+    if (TAIL == 1) gt = lds32(tail_lane);
     if (TAIL == 2) g2[2 * NFULL] = lds64(tail_lane);
   }
 };
 
 __host__ __device__ inline size_t fast_smem_bytes(int N, int MP, int E) {
   size_t s = (size_t)N * MP * 4;            // G table
-  s += (size_t)N * 16;                      // per-site constants {x = log2e 2 sum_j W_ij, y = log2e 2 a_i, fix(x+y), fix(x-y)}
+  s += (size_t)N * 16;                      // per-site constants {x = log2e 2 sum_j W_ij, y = log2e 2 a_i, fix(x), fix(y)}
   s += ((size_t)2 * E + 15) & ~(size_t)15;  // edges (uint8 pairs)
+  s += (size_t)FAST_WARPS * 512;            // proposal records of the current batch, per warp
+  s += (size_t)FAST_WARPS * SIG_STRIDE;     // spins of the warp's chain (bytes, 1 = spin down)
+  s += (size_t)FAST_WARPS * WSTAT * 8;      // statistics scratch per warp
   s += 16 + 32 * 4;                         // mbarrier, reduction scratch
   return s;
 }
@@ -141,69 +178,71 @@ __device__ __forceinline__ uint32_t sw4sel(const uint32_t (&w)[4], int i) {
 }
 
 // Per-chain registers of one warp.
-template <int NP>
+template <int NPA>
 struct ChainRegs {
-  float2 A2[NP], B2[NP];
-  int R;              // fixed-point log2 prod_j (A_j + B_j), summed over the warp
-  uint32_t mybits;    // bit b of lane l: sigma of site 32 b + l is -1
-  uint32_t nacc;
-  int since;          // accepted moves since the last renormalisation
+  float2 A2[NPA], B2[NPA];
+  float At, Bt;          // the scalar unit (TAIL == 1)
+  int R;                 // fixed-point log2 prod_j (A_j + B_j), summed over the warp
+  uint32_t nacc;         // accepted moves of this call
+  uint32_t next_renorm;  // renormalise when nacc reaches this
 };
 
-// lane product prod_q c_q.x * c_q.y with c = X * g + Y
-template <int NP>
-__device__ __forceinline__ float lane_product(const float2 (&X)[NP], const float2 (&Y)[NP], const float2 (&g2)[NP]) {
-  float2 Pa = ffma2(X[0], g2[0], Y[0]);
-  float2 Pb = make_float2(1.0f, 1.0f);
-  if (NP > 1) Pb = ffma2(X[1], g2[1], Y[1]);
+// lane product prod_j (X_j g_j + Y_j) over the lane's units
+template <int NP2, int NPA, bool HAS_T>
+__device__ __forceinline__ float lane_product(const float2 (&X)[NPA], float Xt, const float2 (&Y)[NPA], float Yt, const float2 (&g2)[NPA],
+                                              float gt) {
+  float P = 1.0f;
+  if (NP2 > 0) {
+    float2 Pa = ffma2(X[0], g2[0], Y[0]);
+    float2 Pb = make_float2(1.0f, 1.0f);
+    if (NP2 > 1) Pb = ffma2(X[1], g2[1], Y[1]);
 #pragma unroll
-  for (int q = 2; q < NP; ++q) {
-    const float2 c = ffma2(X[q], g2[q], Y[q]);
-    if (q & 1)
-      Pb = fmul2(Pb, c);
-    else
-      Pa = fmul2(Pa, c);
+    for (int q = 2; q < NP2; ++q) {
+      const float2 c = ffma2(X[q], g2[q], Y[q]);
+      if (q & 1)
+        Pb = fmul2(Pb, c);
+      else
+        Pa = fmul2(Pa, c);
+    }
+    if (NP2 > 1) Pa = fmul2(Pa, Pb);
+    P = Pa.x * Pa.y;
   }
-  return NP > 1 ? (Pa.x * Pa.y) * (Pb.x * Pb.y) : Pa.x * Pa.y;
+  if (HAS_T) {
+    const float ct = fmaf(Xt, gt, Yt);
+    P = NP2 > 0 ? P * ct : ct;
+  }
+  return P;
 }
 
-// One Metropolis proposal on site `site` whose spin has sign POS ? -1 : +1 (nu = -sigma = POS ? +1 : -1).
-// Everything after the lane product is integer: with S = FX_SCALE,
-//   fix(log2 ratio) = (Rp - R) + fix(log2e (2 sum_j W_ij + 2 nu a_i))      and      thr = fix(log2(u) / machine_pow),
-// accept = u < exp(machine_pow * delta)  <=>  thr < fix(log2 ratio)         (netket/sampler/metropolis.py:444-450).
-// Returns true if the state must be renormalised before the next proposal.
-template <int NP, bool POS>
-__device__ __forceinline__ bool propose(ChainRegs<NP> &c, const float2 (&g2)[NP], int rcfix, int thr, int site, int lane) {
-  const float P = POS ? lane_product<NP>(c.B2, c.A2, g2) : lane_product<NP>(c.A2, c.B2, g2);
-  const int Rp = __reduce_add_sync(0xffffffffu, __float2int_rn(lg2_fast(P) * FX_SCALE));
-  if (thr < (int)((uint32_t)Rp - (uint32_t)c.R + (uint32_t)rcfix)) {
-    if (POS) {
+// fixed-point log2 prod_j (A_j + B_j), summed over the warp
+template <int NP2, int NPA, bool HAS_T>
+__device__ __forceinline__ float lane_norm(const ChainRegs<NPA> &c) {
+  float P = 1.0f;
+  if (NP2 > 0) {
+    float2 Pa = fadd2(c.A2[0], c.B2[0]);
 #pragma unroll
-      for (int q = 0; q < NP; ++q) c.B2[q] = fmul2(c.B2[q], g2[q]);
-    } else {
-#pragma unroll
-      for (int q = 0; q < NP; ++q) c.A2[q] = fmul2(c.A2[q], g2[q]);
-    }
-    c.R = Rp;
-    ++c.nacc;
-    ++c.since;
-    if (lane == (site & 31)) c.mybits ^= 1u << (site >> 5);
-    return true;
+    for (int q = 1; q < NP2; ++q) Pa = fmul2(Pa, fadd2(c.A2[q], c.B2[q]));
+    P = Pa.x * Pa.y;
   }
-  return false;
+  if (HAS_T) P *= c.At + c.Bt;
+  return P;
 }
 
 template <int NFULL, int TAIL>
 __global__ void __launch_bounds__(FAST_THREADS, 1)
     sweep_fast_kernel(const __grid_constant__ SweepKernelArgs p, const float *__restrict__ theta_ws, int *__restrict__ flags) {
   using LM = Lanes<NFULL, TAIL>;
-  constexpr int NP = LM::NP, NE = LM::NE, MP = LM::MP;
+  constexpr int NP2 = LM::NP2, NPA = LM::NPA, NE = LM::NE, MP = LM::MP;
+  constexpr bool HAS_T = LM::HAS_T;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int N = p.rbm.N, M = p.rbm.M, E = p.eloc_kind == 1 ? p.ising.n_edges : 0;
   float *Gtab = reinterpret_cast<float *>(smem_raw);
   float4 *rctab = reinterpret_cast<float4 *>(Gtab + (size_t)N * MP);
   uint8_t *edges = reinterpret_cast<uint8_t *>(rctab + N);
-  uint64_t *bar = reinterpret_cast<uint64_t *>(edges + (((size_t)2 * E + 15) & ~(size_t)15));
+  uint4 *rectab = reinterpret_cast<uint4 *>(edges + (((size_t)2 * E + 15) & ~(size_t)15));
+  uint8_t *sigtab = reinterpret_cast<uint8_t *>(rectab + FAST_WARPS * 32);
+  double *wstat = reinterpret_cast<double *>(sigtab + FAST_WARPS * SIG_STRIDE);
+  uint64_t *bar = reinterpret_cast<uint64_t *>(wstat + FAST_WARPS * WSTAT);
   float *red = reinterpret_cast<float *>(bar + 2);
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform by construction: lets ptxas use uniform control flow
@@ -222,6 +261,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1)
     for (int i = 0; i < N; ++i) tma_bulk_g2s(Gtab + (size_t)i * MP, W + (size_t)i * M, (uint32_t)(M * 4), bar);
   }
   for (int e = tid; e < 2 * E; e += FAST_THREADS) edges[e] = (uint8_t)p.ising.edges[e];
+  for (int e = lane; e < WSTAT; e += 32) wstat[warp * WSTAT + e] = 0.0;
   mbar_wait(bar, 0);
   // ---------------- W -> G = exp(-4W) in place; per-site constants; max|W|
   float wmax = 0.0f;
@@ -241,7 +281,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 1)
     rs = warp_sum(rs);
     if (lane == 0) {
       const float x = LOG2E * 2.0f * rs, y = avis != nullptr ? LOG2E * 2.0f * avis[i] : 0.0f;
-      rctab[i] = make_float4(x, y, __int_as_float(__float2int_rn((x + y) * FX_SCALE)), __int_as_float(__float2int_rn((x - y) * FX_SCALE)));
+      if (!(fabsf(y) < 1000.0f)) wmax = __int_as_float(0x7f800000);  // visible bias beyond the fixed-point range: hand over
+      rctab[i] = make_float4(x, y, __int_as_float(__float2int_rn(x * FX_SCALE)), __int_as_float(__float2int_rn(y * FX_SCALE)));
     }
   }
 #pragma unroll
@@ -250,12 +291,12 @@ __global__ void __launch_bounds__(FAST_THREADS, 1)
   __syncthreads();
   wmax = 0.0f;
   for (int w = 0; w < FAST_WARPS; ++w) wmax = fmaxf(wmax, red[w]);
-  // renormalisation period r: A + B = 1 is restored once r accepted moves have piled up, before the next lane product, so
-  // a product (2*NP factors) sees at most r - 1 un-normalised accepts: factors within G^(+-r) of 1.  2 NP r 4 wmax log2(e)
-  // must stay below the fp32 exponent range (and 32 lanes of it, times FX_SCALE, inside int32)
+  // renormalisation period r: A + B = 1 is restored as soon as r accepted moves have piled up, so a product (2*NP factors)
+  // sees at most r - 1 un-normalised accepts: factors within G^(+-r) of 1.  2 NP r 4 wmax log2(e) must stay below the fp32
+  // exponent range (and 32 lanes of it, times FX_SCALE, inside int32)
   int renorm = 0;
   {
-    const float per = (float)(2 * NP) * 4.0f * wmax * LOG2E;
+    const float per = (float)(2 * ((NE + 1) / 2)) * 4.0f * wmax * LOG2E;
     renorm = 32;
     while (renorm >= 1 && (float)renorm * per > EXP_RANGE) renorm >>= 1;
     if (!(wmax < 1.0e30f)) renorm = 0;  // NaN / Inf weights
@@ -264,7 +305,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1)
     if (blockIdx.x == 0 && tid == 0) flags[0] = 1;
     return;
   }
-  
+
   const int T_total = (p.n_discard + p.chain_length) * p.sweep_size;
   const float hh = (float)p.ising.h, JJ = (float)p.ising.J;
   // loop-invariant values the hot loop needs, made opaque so that they stay in registers instead of being
@@ -272,30 +313,40 @@ __global__ void __launch_bounds__(FAST_THREADS, 1)
   float pw = (float)p.machine_pow;
   const float inv_pw = pw > 0.0f ? 1.0f / pw : 0.0f;
   uint32_t rc_s = smem_u32(rctab);
-  uint32_t lane_row = smem_u32(Gtab) + 16u * lane;                         // + site * MP * 4
-  uint32_t lane_tail = smem_u32(Gtab) + 512u * NFULL + 4u * TAIL * lane;   // + site * MP * 4
+  const uint32_t g_s = smem_u32(Gtab);
+  uint32_t lane16 = 16u * lane;                             // + row address
+  uint32_t tailoff = 512u * NFULL + 4u * TAIL * lane;       // + row address
+  uint32_t rec_s = smem_u32(rectab) + 512u * warp;
+  uint32_t sig_s = smem_u32(sigtab) + (uint32_t)SIG_STRIDE * warp;
   int sweep_size = p.sweep_size;
   int lane_o = lane;
-  asm volatile("" : "+r"(rc_s), "+r"(lane_row), "+r"(lane_tail), "+r"(sweep_size), "+r"(lane_o));
+  asm volatile("" : "+r"(rc_s), "+r"(lane16), "+r"(tailoff), "+r"(sweep_size), "+r"(lane_o), "+r"(rec_s), "+r"(sig_s));
+  double *ws = wstat + warp * WSTAT;  // [0..7] partial sums of this warp's chains, [8] block sum, [9] / [10] half sums, [11] chain sum
+  const bool want_stats = p.stats_out != nullptr && p.eloc_kind == 1;
+  const int L = p.chain_length;
+  const int l_block = (L / 32) > 1 ? (L / 32) : 1;  // mc_stats_old.py:100
+  const int n_b = L / l_block, half = L / 2;
 
   // chains are dealt out warp-major (round r gives warp w of CTA b the chain (r * FAST_WARPS + w) * gridDim + b): the chains of
   // the last, partial round (2^16 chains = 15.8 rounds of 148 x 28 warps) then thin out every SM equally instead of leaving
   // whole SMs idle while the others run a full round
   for (int chain = warp * gridDim.x + blockIdx.x; chain < (int)p.B; chain += gridDim.x * FAST_WARPS) {
-    ChainRegs<NP> c;
-    // ---- sigma, lane-distributed: lane l keeps the bits of sites l, 32 + l, 64 + l, 96 + l
-    c.mybits = 0;
+    ChainRegs<NPA> c;
+    // ---- sigma as bytes in shared memory (1 = spin down); every lane performs every later store itself
+    __syncwarp();
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
       const int idx = 32 * b + lane;
-      if (idx < N && p.sigma[(size_t)chain * N + idx] < 0) c.mybits |= 1u << b;
+      if (idx < N) sts_u8(sig_s + idx, p.sigma[(size_t)chain * N + idx] < 0 ? 1u : 0u);
     }
     // ---- theta (from the GEMM) -> (A, B) = (e^theta, e^-theta) / (2 cosh theta)
     {
       const float *th = theta_ws + (size_t)chain * M;
+      c.At = 0.5f;
+      c.Bt = 0.5f;
 #pragma unroll
-      for (int e = 0; e < 2 * NP; ++e) {
-        const int j = e < NE ? LM::unit(e, lane) : M;
+      for (int e = 0; e < NE; ++e) {
+        const int j = LM::unit(e, lane);
         float av = 0.5f, bv = 0.5f;  // padding units: theta = 0
         if (j < M) {
           const float x = th[j];
@@ -304,122 +355,129 @@ __global__ void __launch_bounds__(FAST_THREADS, 1)
           av = x >= 0.0f ? big : small;
           bv = x >= 0.0f ? small : big;
         }
-        if (e & 1) {
-          c.A2[e >> 1].y = av;
-          c.B2[e >> 1].y = bv;
+        if (e < 2 * NP2) {
+          if (e & 1) {
+            c.A2[e >> 1].y = av;
+            c.B2[e >> 1].y = bv;
+          } else {
+            c.A2[e >> 1].x = av;
+            c.B2[e >> 1].x = bv;
+          }
         } else {
-          c.A2[e >> 1].x = av;
-          c.B2[e >> 1].x = bv;
+          c.At = av;
+          c.Bt = bv;
         }
       }
     }
-    c.R = 0;
     c.nacc = 0;
-    c.since = 0;
+    c.next_renorm = (uint32_t)renorm;
     int in_sweep = 0, sweep_idx = 0;
     const uint64_t gchain = p.chain_offset + (uint64_t)chain;
+    __syncwarp();
 
-    auto renormalise = [&]() {  // A + B = 1
+    auto renormalise = [&]() {  // A + B = 1 (approximately: R is re-measured, not assumed)
 #pragma unroll
-      for (int q = 0; q < NP; ++q) {
-        const float ix = __frcp_rn(c.A2[q].x + c.B2[q].x), iy = __frcp_rn(c.A2[q].y + c.B2[q].y);
-        c.A2[q] = fmul2(c.A2[q], make_float2(ix, iy));
-        c.B2[q] = fmul2(c.B2[q], make_float2(ix, iy));
+      for (int q = 0; q < NP2; ++q) {
+        const float2 s2 = fadd2(c.A2[q], c.B2[q]);
+        const float2 i2 = make_float2(rcp_fast(s2.x), rcp_fast(s2.y));
+        c.A2[q] = fmul2(c.A2[q], i2);
+        c.B2[q] = fmul2(c.B2[q], i2);
       }
-      c.R = 0;
-      c.since = 0;
+      if (HAS_T) {
+        const float it = rcp_fast(c.At + c.Bt);
+        c.At *= it;
+        c.Bt *= it;
+      }
+      c.R = __reduce_add_sync(0xffffffffu, __float2int_rn(lg2_fast(lane_norm<NP2, NPA, HAS_T>(c)) * FX_SCALE));
+      c.next_renorm = c.nacc + (uint32_t)renorm;
     };
+    c.R = __reduce_add_sync(0xffffffffu, __float2int_rn(lg2_fast(lane_norm<NP2, NPA, HAS_T>(c)) * FX_SCALE));
     // log psi of the current state from (A, B): lncosh(theta_j) = log((A_j + B_j) / (2 sqrt(A_j B_j)))
     auto logpsi_now = [&]() -> float {
       float acc2 = 0.0f;  // log2 units
 #pragma unroll
-      for (int q = 0; q < NP; ++q) {
+      for (int q = 0; q < NP2; ++q) {
         acc2 += log2f(c.A2[q].x + c.B2[q].x) - 0.5f * (log2f(c.A2[q].x) + log2f(c.B2[q].x)) - 1.0f;
         acc2 += log2f(c.A2[q].y + c.B2[q].y) - 0.5f * (log2f(c.A2[q].y) + log2f(c.B2[q].y)) - 1.0f;
       }
+      if (HAS_T) acc2 += log2f(c.At + c.Bt) - 0.5f * (log2f(c.At) + log2f(c.Bt)) - 1.0f;
       float vis2 = 0.0f;  // log2e * sum_i a_i sigma_i
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
         const int idx = 32 * b + lane;
-        if (idx < N) vis2 += ((c.mybits >> b) & 1u) ? -0.5f * rctab[idx].y : 0.5f * rctab[idx].y;
+        if (idx < N) vis2 += lds_u8(sig_s + idx) ? -0.5f * rctab[idx].y : 0.5f * rctab[idx].y;
       }
       return LN2 * warp_sum(acc2 + vis2);
     };
 
     for (int tt = 0; tt < T_total; tt += 32) {
-      // ---- 32 proposals' worth of randomness, one Philox call per lane: site and thr = fix(log2(u) / machine_pow)
-      int site_l = 0, thr_l = 0;
-      if (tt + lane < T_total) {
-        uint32_t w0;
-        float u;
-        if (p.stream_w0 != nullptr) {
-          w0 = p.stream_w0[(size_t)(tt + lane) * p.B + chain];
-          u = reinterpret_cast<const float *>(p.stream_u)[(size_t)(tt + lane) * p.B + chain];
-        } else {
-          const uint4 w = philox_words(p.seed, p.t0 + (uint64_t)(tt + lane), gchain, STREAM_STEP);
-          w0 = w.x;
-          u = uniform_from_words<float>(w);
+      // ---- 32 proposals' worth of randomness, one Philox call per lane; the lane leaves the proposal's record
+      //      {row address, spin address, fix(log2(u) / machine_pow) - fix(x_site), fix(y_site)} in shared memory
+      {
+        int site_l = 0, thr_l = 0;
+        if (tt + lane < T_total) {
+          uint32_t w0;
+          float u;
+          if (p.stream_w0 != nullptr) {
+            w0 = p.stream_w0[(size_t)(tt + lane) * p.B + chain];
+            u = reinterpret_cast<const float *>(p.stream_u)[(size_t)(tt + lane) * p.B + chain];
+          } else {
+            const uint4 w = philox_words(p.seed, p.t0 + (uint64_t)(tt + lane), gchain, STREAM_STEP);
+            w0 = w.x;
+            u = uniform_from_words<float>(w);
+          }
+          site_l = (int)__umulhi(w0, (uint32_t)N);
+          // u == 0 or machine_pow == 0: always accept
+          const float t2 = (pw > 0.0f && u > 0.0f) ? log2f(u) * inv_pw * FX_SCALE : (float)THR_MIN;
+          thr_l = __float2int_rn(fmaxf(t2, (float)THR_MIN));
         }
-        site_l = (int)__umulhi(w0, (uint32_t)N);
-        // u == 0 or machine_pow == 0: always accept
-        const float t2 = (pw > 0.0f && u > 0.0f) ? log2f(u) * inv_pw * FX_SCALE : -2.0e9f;
-        thr_l = __float2int_rn(fmaxf(t2, -2.0e9f));
+        const float4 rc = lds128(rc_s + 16u * site_l);
+        uint4 rec;
+        rec.x = g_s + (uint32_t)site_l * (uint32_t)(MP * 4);
+        rec.y = sig_s + (uint32_t)site_l;
+        rec.z = (uint32_t)thr_l - (uint32_t)__float_as_int(rc.z);
+        rec.w = (uint32_t)__float_as_int(rc.w);
+        __syncwarp();
+        sts128u(rec_s + 16u * lane_o, rec);
+        __syncwarp();
       }
       const int nb = min(32, T_total - tt);
       int k = 0;
       while (k < nb) {
-        // a segment = proposals up to the end of the sweep / of this batch; rows are prefetched one proposal ahead
+        // a segment = proposals up to the end of the sweep / of this batch
         const int kend = k + min(nb - k, sweep_size - in_sweep);
         in_sweep += kend - k;
-        // software pipeline: while proposal k runs, the G row, the threshold, the per-site constants and the spin of
-        // proposal k+1 are already in flight; the prefetched spin is patched if proposal k flips that very site
-        float2 gA[NP], gB[NP];
-        int siteA, siteB, thrA, thrB;
-        uint32_t ownA, ownB;
-        float2 rcA, rcB;
-#define NK_FETCH(G, SITE, THR, OWN, RC, KK)                                            \
-  {                                                                                    \
-    SITE = __shfl_sync(0xffffffffu, site_l, (KK));                                     \
-    const uint32_t roff = (uint32_t)SITE * (uint32_t)(MP * 4);                         \
-    LM::load_row(lane_row + roff, lane_tail + roff, G);                                \
-    RC = lds64(rc_s + 16u * SITE + 8u);                                                \
-    THR = __shfl_sync(0xffffffffu, thr_l, (KK));                                       \
-    OWN = __shfl_sync(0xffffffffu, c.mybits, SITE & 31);                               \
-  }
-#define NK_STEP(G, SITE, THR, OWN, RC, NSITE, NOWN)                                    \
-  {                                                                                    \
-    if (c.since >= renorm) renormalise();                                              \
-    const bool acc = ((OWN >> (SITE >> 5)) & 1u)                                       \
-                         ? propose<NP, true>(c, G, __float_as_int(RC.x), THR, SITE, lane_o)   \
-                         : propose<NP, false>(c, G, __float_as_int(RC.y), THR, SITE, lane_o); \
-    if (acc && ((SITE ^ NSITE) & 31) == 0) NOWN ^= 1u << (SITE >> 5);                  \
-  }
-#if NK_FAST_PREFETCH
-        NK_FETCH(gA, siteA, thrA, ownA, rcA, k)
-        for (; k + 1 < kend; k += 2) {
-          NK_FETCH(gB, siteB, thrB, ownB, rcB, k + 1)
-          NK_STEP(gA, siteA, thrA, ownA, rcA, siteB, ownB)
-          NK_FETCH(gA, siteA, thrA, ownA, rcA, k + 2)  // beyond the batch: lanes hold site 0, a harmless prefetch
-          NK_STEP(gB, siteB, thrB, ownB, rcB, siteA, ownA)
-        }
-        if (k < kend) {
-          siteB = 32;  // no successor to patch
-          ownB = 0;
-          NK_STEP(gA, siteA, thrA, ownA, rcA, siteB, ownB)
-          ++k;
-        }
-#else
-        // measured on B200: resident warps matter more than row prefetch (28 warps x 72 registers beats 20 x 96)
-        (void)gB; (void)thrB; (void)rcB;
         for (; k < kend; ++k) {
-          NK_FETCH(gA, siteA, thrA, ownA, rcA, k)
-          siteB = 32;
-          ownB = 0;
-          NK_STEP(gA, siteA, thrA, ownA, rcA, siteB, ownB)
+          const uint4 rec = lds128u(rec_s + 16u * k);
+          const uint32_t sdown = lds_u8(rec.y);
+          float2 g2[NPA];
+          float gt = 1.0f;
+          LM::load_row(rec.x + lane16, rec.x + tailoff, g2, gt);
+          // spin down (nu = +1): prod (B g + A), accept B <- B g;   spin up (nu = -1): prod (A g + B), accept A <- A g
+          if (sdown) {
+            const float P = lane_product<NP2, NPA, HAS_T>(c.B2, c.Bt, c.A2, c.At, g2, gt);
+            const int Rp = __reduce_add_sync(0xffffffffu, __float2int_rn(lg2_fast(P) * FX_SCALE));
+            if ((int)rec.z < (int)((uint32_t)Rp - (uint32_t)c.R + rec.w)) {
+#pragma unroll
+              for (int q = 0; q < NP2; ++q) c.B2[q] = fmul2(c.B2[q], g2[q]);
+              if (HAS_T) c.Bt *= gt;
+              c.R = Rp;
+              sts_u8(rec.y, 0u);
+              if (++c.nacc == c.next_renorm) renormalise();
+            }
+          } else {
+            const float P = lane_product<NP2, NPA, HAS_T>(c.A2, c.At, c.B2, c.Bt, g2, gt);
+            const int Rp = __reduce_add_sync(0xffffffffu, __float2int_rn(lg2_fast(P) * FX_SCALE));
+            if ((int)rec.z < (int)((uint32_t)Rp - (uint32_t)c.R - rec.w)) {
+#pragma unroll
+              for (int q = 0; q < NP2; ++q) c.A2[q] = fmul2(c.A2[q], g2[q]);
+              if (HAS_T) c.At *= gt;
+              c.R = Rp;
+              sts_u8(rec.y, 1u);
+              if (++c.nacc == c.next_renorm) renormalise();
+            }
+          }
         }
-#endif
-#undef NK_STEP
-#undef NK_FETCH
         if (in_sweep == sweep_size) {
           in_sweep = 0;
           const int sw = sweep_idx - p.n_discard;
@@ -430,7 +488,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1)
 #pragma unroll
               for (int b = 0; b < 4; ++b) {
                 const int idx = 32 * b + lane;
-                if (idx < N) p.samples_out[o * N + idx] = ((c.mybits >> b) & 1u) ? (int8_t)-1 : (int8_t)1;
+                if (idx < N) p.samples_out[o * N + idx] = lds_u8(sig_s + idx) ? (int8_t)-1 : (int8_t)1;
               }
             }
             if (p.logp_out != nullptr) {
@@ -443,16 +501,25 @@ __global__ void __launch_bounds__(FAST_THREADS, 1)
 #pragma unroll
               for (int e = 0; e < NE; ++e) {
                 const int j = LM::unit(e, lane);
-                const float av = (e & 1) ? c.A2[e >> 1].y : c.A2[e >> 1].x, bv = (e & 1) ? c.B2[e >> 1].y : c.B2[e >> 1].x;
+                float av, bv;
+                if (e < 2 * NP2) {
+                  av = (e & 1) ? c.A2[e >> 1].y : c.A2[e >> 1].x;
+                  bv = (e & 1) ? c.B2[e >> 1].y : c.B2[e >> 1].x;
+                } else {
+                  av = c.At;
+                  bv = c.Bt;
+                }
                 if (j < M) to[j] = __fdividef(av - bv, av + bv);
               }
             }
             if (p.eloc_kind == 1) {
               // E_loc = J sum_<ij> s_i s_j - h sum_i exp(delta_i)
-              if (c.since >= renorm) renormalise();  // the flips below must see at most r - 1 un-normalised accepts too
               uint32_t sw4[4];
 #pragma unroll
-              for (int b = 0; b < 4; ++b) sw4[b] = __ballot_sync(0xffffffffu, (c.mybits >> b) & 1u);
+              for (int b = 0; b < 4; ++b) {
+                const int idx = 32 * b + lane;
+                sw4[b] = __ballot_sync(0xffffffffu, idx < N && lds_u8(sig_s + idx) != 0u);
+              }
               int zz = 0;
               for (int e = lane; e < E; e += 32) {
                 const int a = edges[2 * e], bq = edges[2 * e + 1];
@@ -464,27 +531,25 @@ __global__ void __launch_bounds__(FAST_THREADS, 1)
               float off = 0.0f;
               if (hh != 0.0f) {
                 // accurate (float) normalisation log2 prod_j (A_j + B_j) for this sample
-                float nrm = 1.0f;
-#pragma unroll
-                for (int q = 0; q < NP; ++q) nrm *= (c.A2[q].x + c.B2[q].x) * (c.A2[q].y + c.B2[q].y);
-                const float Rf = warp_sum(lg2_fast(nrm));
+                const float Rf = warp_sum(lg2_fast(lane_norm<NP2, NPA, HAS_T>(c)));
                 // sites in groups of 16: 16 independent lane products (ILP), then a transposed butterfly that needs
                 // 16 shuffles for 16 sites instead of 80; lane l ends up with the total of site base + ((l >> 1) & 15)
                 float off_l = 0.0f;
                 const int myidx = (lane_o >> 1) & 15;
-#pragma unroll 1
-                for (int base = 0; base < N; base += 16) {
+                auto group = [&](const int base, const bool full) {
                   const uint32_t word = sw4sel(sw4, base >> 5) >> (base & 16);
                   float v[16];
 #pragma unroll
                   for (int jj = 0; jj < 16; ++jj) {
                     const int sidx = base + jj;
                     v[jj] = 0.0f;
-                    if (sidx < N) {
-                      const uint32_t so = (uint32_t)sidx * (uint32_t)(MP * 4);
-                      float2 r2[NP];
-                      LM::load_row(lane_row + so, lane_tail + so, r2);
-                      const float Ps = ((word >> jj) & 1u) ? lane_product<NP>(c.B2, c.A2, r2) : lane_product<NP>(c.A2, c.B2, r2);
+                    if (full || sidx < N) {
+                      const uint32_t so = g_s + (uint32_t)sidx * (uint32_t)(MP * 4);
+                      float2 r2[NPA];
+                      float rt = 1.0f;
+                      LM::load_row(so + lane16, so + tailoff, r2, rt);
+                      const float Ps = ((word >> jj) & 1u) ? lane_product<NP2, NPA, HAS_T>(c.B2, c.Bt, c.A2, c.At, r2, rt)
+                                                            : lane_product<NP2, NPA, HAS_T>(c.A2, c.At, c.B2, c.Bt, r2, rt);
                       v[jj] = lg2_fast(Ps);
                     }
                   }
@@ -500,16 +565,41 @@ __global__ void __launch_bounds__(FAST_THREADS, 1)
                   }
                   const float tot = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
                   const int mys = base + myidx;
-                  if (mys < N && (lane_o & 1) == 0) {
+                  if ((full || mys < N) && (lane_o & 1) == 0) {
                     const float2 rcs = lds64(rc_s + 16u * mys);
                     const float cst = ((word >> myidx) & 1u) ? rcs.x + rcs.y : rcs.x - rcs.y;
                     off_l += ex2_fast(tot - Rf + cst);
                   }
-                }
+                };
+                int base = 0;
+#pragma unroll 1
+                for (; base + 16 <= N; base += 16) group(base, true);
+                if (base < N) group(base, false);
                 off = warp_sum(off_l);
               }
               const float e_loc = JJ * (float)zz - hh * off;
-              if (lane == 0) store_as<float>(p.eloc_out, o, e_loc, p.eloc_dtype);
+              if (lane == 0) {
+                store_as<float>(p.eloc_out, o, e_loc, p.eloc_dtype);
+                if (want_stats) {
+                  // shifted sums of mc_stats_old.py:87-196 (the layout of nk_stats_partial's phase 1)
+                  const double d = (double)e_loc - p.stats_shift;
+                  ws[0] += d * d;
+                  ws[11] += d;
+                  if (sw < n_b * l_block) {
+                    ws[8] += d;
+                    if ((sw + 1) % l_block == 0) {
+                      const double m = ws[8] / (double)l_block;
+                      ws[3] += m;
+                      ws[4] += m * m;
+                      ws[8] = 0.0;
+                    }
+                  }
+                  if (sw < half)
+                    ws[9] += d;
+                  else if (sw < 2 * half)
+                    ws[10] += d;
+                }
+              }
             }
           }
         }
@@ -519,12 +609,32 @@ __global__ void __launch_bounds__(FAST_THREADS, 1)
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
       const int idx = 32 * b + lane;
-      if (idx < N) p.sigma[(size_t)chain * N + idx] = ((c.mybits >> b) & 1u) ? (int8_t)-1 : (int8_t)1;
+      if (idx < N) p.sigma[(size_t)chain * N + idx] = lds_u8(sig_s + idx) ? (int8_t)-1 : (int8_t)1;
     }
     const float lp = logpsi_now();
     if (lane == 0) {
       reinterpret_cast<float *>(p.log_prob)[chain] = (float)p.machine_pow * lp;
       p.n_accepted[chain] += (int64_t)c.nacc;
+      if (want_stats && L > 0) {
+        const double m = ws[11] / (double)L;
+        ws[1] += m;
+        ws[2] += m * m;
+        ws[7] += ws[11];
+        if (half > 0) {
+          const double ha = ws[9] / (double)half, hb = ws[10] / (double)half;
+          ws[5] += ha + hb;
+          ws[6] += ha * ha + hb * hb;
+        }
+        ws[9] = ws[10] = ws[11] = 0.0;
+      }
+    }
+  }
+  if (want_stats) {  // one atomic per CTA and partial sum
+    __syncthreads();
+    if (tid < NK_STATS_NPARTIAL) {
+      double s = 0.0;
+      for (int w = 0; w < FAST_WARPS; ++w) s += wstat[w * WSTAT + tid];
+      atomicAdd(p.stats_out + tid, s);
     }
   }
 }
@@ -559,7 +669,6 @@ bool sweep_fast_supported(const SweepKernelArgs &a) {
   if (a.rbm.dtype != NK_F32 || a.rule != NK_RULE_LOCAL) return false;
   if (a.rbm.N > 128 || !fast_shape(a.rbm.M, &fs)) return false;
   if (a.eloc_kind == 2) return false;
-  if (a.eloc_kind == 1 && a.rbm.N > 256) return false;
   const int E = a.eloc_kind == 1 ? a.ising.n_edges : 0;
   if (fast_smem_bytes(a.rbm.N, fs.mp, E) > 227 * 1024) return false;
   if ((size_t)a.rbm.N * a.rbm.M * 4 >= (1u << 20)) return false;  // mbarrier tx-count range

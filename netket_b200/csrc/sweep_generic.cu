@@ -31,6 +31,32 @@ __device__ __forceinline__ int warp_select_hoppable(const int8_t *sig, const int
   return -1;
 }
 
+// ExchangeRule(probabilities=p) (rules/exchange.py:155-182): total weight sum_c hoppable_c p_c ...
+__device__ __forceinline__ double warp_weight_hoppable(const int8_t *sig, const int32_t *clusters, const double *prob, int C, int lane) {
+  double w = 0.0;
+  for (int c = lane; c < C; c += 32) w += (sig[clusters[2 * c]] != sig[clusters[2 * c + 1]]) ? prob[c] : 0.0;
+  return warp_sum(w);
+}
+
+// ... and the first cluster (in cluster order) whose running weight reaches r: jax.random.choice's inverse-CDF pick,
+// searchsorted(cumsum(hoppable * p), r)
+__device__ __forceinline__ int warp_select_weighted(const int8_t *sig, const int32_t *clusters, const double *prob, int C, double r, int lane) {
+  double run = 0.0;
+  for (int base = 0; base < C; base += 32) {
+    const int c = base + lane;
+    double w = (c < C && sig[clusters[2 * c]] != sig[clusters[2 * c + 1]]) ? prob[c] : 0.0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double t = __shfl_up_sync(0xffffffffu, w, d);
+      if (lane >= d) w += t;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, c < C && run + w >= r);
+    if (m != 0u) return base + __ffs(m) - 1;
+    run += __shfl_sync(0xffffffffu, w, 31);
+  }
+  return C - 1;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) sweep_generic_kernel(const __grid_constant__ SweepKernelArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -88,12 +114,19 @@ __global__ void __launch_bounds__(256) sweep_generic_kernel(const __grid_constan
           }
           __syncwarp();
         } else {
-          // ExchangeRule.transition (rules/exchange.py:143-184), probabilities=None
+          // ExchangeRule.transition (rules/exchange.py:143-184)
           const int C = p.n_clusters;
-          const int n_hop = warp_count_hoppable(sig, p.clusters, C, lane);
-          if (n_hop > 0) {
-            const int kth = (int)__umulhi(w0, (uint32_t)n_hop);
-            const int c = warp_select_hoppable(sig, p.clusters, C, kth, lane);
+          const bool weighted = p.cluster_probs != nullptr;
+          const int n_hop = weighted ? 0 : warp_count_hoppable(sig, p.clusters, C, lane);
+          const double w_hop = weighted ? warp_weight_hoppable(sig, p.clusters, p.cluster_probs, C, lane) : 0.0;
+          if (weighted ? w_hop > 0.0 : n_hop > 0) {
+            int c;
+            if (weighted) {
+              c = warp_select_weighted(sig, p.clusters, p.cluster_probs, C, w_hop * (((double)w0 + 0.5) * 2.3283064365386963e-10), lane);
+            } else {
+              const int kth = (int)__umulhi(w0, (uint32_t)n_hop);
+              c = warp_select_hoppable(sig, p.clusters, C, kth, lane);
+            }
             const int si = p.clusters[2 * c], sj = p.clusters[2 * c + 1];
             const T vi = (T)sig[si], vj = (T)sig[sj];
             const T di = vj - vi, dj = vi - vj;  // sigma' - sigma
@@ -107,8 +140,14 @@ __global__ void __launch_bounds__(256) sweep_generic_kernel(const __grid_constan
               sig[sj] = tmp;
             }
             __syncwarp();
-            const int n_hop_p = warp_count_hoppable(sig, p.clusters, C, lane);
-            const T corr = Math<T>::log((T)n_hop) - Math<T>::log((T)n_hop_p);
+            T corr;
+            if (weighted) {
+              const double w_hop_p = warp_weight_hoppable(sig, p.clusters, p.cluster_probs, C, lane);
+              corr = (T)(log(w_hop) - log(w_hop_p));
+            } else {
+              const int n_hop_p = warp_count_hoppable(sig, p.clusters, C, lane);
+              corr = Math<T>::log((T)n_hop) - Math<T>::log((T)n_hop_p);
+            }
             const bool accept = u < Math<T>::exp(pw * delta + corr);
             if (accept) {
               warp_theta_update_two(r, theta, si, di, sj, dj, lane);

@@ -103,6 +103,7 @@ def cg(A, b, x0=None, *, tol=1e-5, atol=0.0, maxiter=None):
     defaulting to 10 x size).  ``A`` is a callable on flat float64 device vectors.  Returns ``(x, info)`` with
     ``info = {"n_iter", "residual"}``."""
     x = torch.zeros_like(b) if x0 is None else x0.clone()
+    default_cap = maxiter is None
     if maxiter is None:
         maxiter = 10 * b.numel()
     bs = float(torch.dot(b, b))
@@ -110,6 +111,7 @@ def cg(A, b, x0=None, *, tol=1e-5, atol=0.0, maxiter=None):
     r = b - A(x) if x0 is not None else b.clone()
     p = r.clone()
     gamma = float(torch.dot(r, r))
+    best = gamma
     k = 0
     while gamma > stop2 and k < maxiter:
         Ap = A(p)
@@ -120,7 +122,17 @@ def cg(A, b, x0=None, *, tol=1e-5, atol=0.0, maxiter=None):
         p.mul_(gamma_new / gamma).add_(r)
         gamma = gamma_new
         k += 1
-    return x, {"n_iter": k, "residual": gamma ** 0.5}
+        if default_cap and k >= 2000 and gamma > stop2 and gamma >= 0.25 * best:
+            # no factor-2 progress of |r| over the last 1000 iterations: the operator is only consistent to its working
+            # precision (fp32 matvec) and the recurrence has stagnated above `tol`; stop instead of running to 10 x size
+            import warnings
+
+            warnings.warn(f"cg stagnated at |r| = {gamma ** 0.5:.3e} (target {stop2 ** 0.5:.3e}) after {k} iterations", RuntimeWarning,
+                          stacklevel=2)
+            break
+        if k % 1000 == 0:
+            best = gamma
+    return x, {"n_iter": k, "residual": gamma ** 0.5, "converged": gamma <= stop2}
 
 
 # ------------------------------------------------------------------------------------------------ QGT

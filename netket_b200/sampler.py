@@ -4,7 +4,7 @@ Mirrors the ``Sampler`` seam S1 (netket/sampler/base.py:254-463, netket/sampler/
 ``init_state / reset / sample / samples / sample_next``, functional state updates (inputs are never mutated),
 ``n_chains`` rounded up to a multiple of the number of ranks with a warning (metropolis.py:179-203,296-302),
 ``sweep_size`` default = hilbert.size (:283-284), 16 chains per rank by default (:287-289), ``machine_pow`` real
-and >= 0 (base.py:139-150).  Only ``LocalRule`` and ``ExchangeRule`` (``probabilities=None``) exist: any other
+and >= 0 (base.py:139-150).  Only ``LocalRule`` and ``ExchangeRule`` (uniform or ``probabilities=``) exist: any other
 rule raises — there is no generic/CPU fallback.
 
 Multi-GPU: one process per GPU (torch.distributed); this rank owns chains
@@ -52,18 +52,33 @@ class ExchangeRule(MetropolisRule):
     code = _lib.NK_RULE_EXCHANGE
 
     def __init__(self, *, clusters=None, graph=None, d_max=1, probabilities=None):
-        if probabilities is not None:
-            raise NotImplementedError("ExchangeRule(probabilities=...) is not implemented by the fused kernel")
+        if probabilities is not None:  # exchange.py:112-115
+            probabilities = np.atleast_1d(np.asarray(probabilities, dtype=np.float64))
+            if not np.all(probabilities > 0):
+                raise ValueError("Probabilities must be positive")
         if clusters is None and graph is not None:
             D = np.asarray(graph.distances())
             cl = np.argwhere(D <= d_max)
             clusters = cl[cl[:, 0] < cl[:, 1]]
+            if probabilities is not None:  # one weight per graph distance (compute_clusters, :200-203)
+                assert probabilities.shape == (d_max,), f"Expected {d_max = } probabilities, got {probabilities}"
+                probabilities = probabilities[D[clusters[:, 0], clusters[:, 1]] - 1]
         elif not (clusters is not None and graph is None):
             raise ValueError("You must either provide the list of exchange-clusters or a netket graph, from which "
                              "clusters will be computed using the maximum distance d_max. ")
         self.clusters = np.ascontiguousarray(np.asarray(clusters, dtype=np.int32).reshape(-1, 2))
-        self.probabilities = None
+        if probabilities is not None and len(probabilities) != len(self.clusters):
+            raise TypeError(f"Number of clusters and probabilities don't match: {len(self.clusters)} != {len(probabilities)}")
+        self.probabilities = None if probabilities is None else np.ascontiguousarray(probabilities, dtype=np.float64)
         self._dev = {}
+
+    def probabilities_on(self, device):
+        if self.probabilities is None:
+            return None
+        k = ("p", str(device))
+        if k not in self._dev:
+            self._dev[k] = torch.from_numpy(self.probabilities).to(device)
+        return self._dev[k]
 
     def clusters_on(self, device):
         k = str(device)
@@ -94,12 +109,15 @@ class MetropolisSamplerState:
 
     @property
     def n_steps(self):
-        """Total number of moves performed across all ranks since the last reset (:121-124)."""
+        """Total number of moves performed across all ranks since the last reset (:121-124); every rank runs the same
+        launches, so this is the per-process counter times the number of ranks."""
         _, ws = world()
         return self.n_steps_proc * ws
 
     @property
     def n_accepted(self):
+        """Accepted moves summed over all ranks.  COLLECTIVE under torch.distributed (one all-reduce): call it on every
+        rank; ``repr`` and logging on a single rank should use ``acceptance_proc``."""
         from .stats import _allreduce
 
         s = self.n_accepted_proc.sum().to(torch.float64).reshape(1)
@@ -107,15 +125,24 @@ class MetropolisSamplerState:
 
     @property
     def acceptance(self):
-        """Fraction of accepted moves since the last reset; None before any sampling (:97-108)."""
+        """Fraction of accepted moves since the last reset; None before any sampling (:97-108).  Collective, like
+        ``n_accepted``."""
         if self.n_steps == 0:
             return None
         return self.n_accepted / self.n_steps
 
-    def __repr__(self):
+    @property
+    def acceptance_proc(self):
+        """Acceptance over this rank's chains only (no communication)."""
+        if self.n_steps_proc == 0:
+            return None
+        return int(self.n_accepted_proc.sum().item()) / self.n_steps_proc
+
+    def __repr__(self):  # per-rank counters: printing a state on one rank must not start a collective
         if self.n_steps_proc > 0:
-            return (f"MetropolisSamplerState(# accepted = {self.n_accepted}/{self.n_steps} "
-                    f"({self.acceptance * 100}%), rng state={self.rng})")
+            na = int(self.n_accepted_proc.sum().item())
+            return (f"MetropolisSamplerState(# accepted = {na}/{self.n_steps_proc} "
+                    f"({na / self.n_steps_proc * 100}%), rng state={self.rng})")
         return f"MetropolisSamplerState(rng state={self.rng})"
 
 
@@ -234,9 +261,12 @@ class MetropolisSampler:
         return state.replace(σ=sigma, log_prob=log_prob, n_steps_proc=0, n_accepted_proc=torch.zeros_like(state.n_accepted_proc))
 
     def _launch(self, machine, parameters, state, chain_length, *, n_discard=0, return_log_probabilities=False,
-                operator=None, stream=None, path=_lib.NK_PATH_AUTO, want_samples=True, tanh_out=None):
+                operator=None, stream=None, path=_lib.NK_PATH_AUTO, want_samples=True, tanh_out=None, stats_shift=None):
         """One ``nk_sweep`` call.  Returns (samples, logp|None, eloc|None, new_state).  ``tanh_out``: optional tensor
-        ``(B, chain_length, M)`` that receives tanh(theta) of every recorded sample (input of ``nk_forces_rbm``)."""
+        ``(B, chain_length, M)`` that receives tanh(theta) of every recorded sample (input of ``nk_forces_rbm``).
+        ``stats_shift``: with an operator, also reduce the statistics' partial sums inside the launch (shifted by this
+        estimate of the mean); the return value then has a fifth element, a float64 device tensor
+        ``[NK_STATS_NPARTIAL sums | n_chains of this rank]`` ready for ONE all-reduce."""
         self._check_machine(machine)
         rbm = RBM.c_struct(parameters)
         N = self.hilbert.size
@@ -276,6 +306,9 @@ class MetropolisSampler:
         if isinstance(self.rule, ExchangeRule):
             cl = self.rule.clusters_on(dev)
             a.clusters, a.n_clusters = cl.data_ptr(), int(cl.shape[0])
+            pr = self.rule.probabilities_on(dev)
+            if pr is not None:
+                a.cluster_probs = pr.data_ptr()
         a.path = path
         if tanh_out is not None:
             if tuple(tanh_out.shape) != (B, chain_length, rbm.M) or tanh_out.dtype != W.dtype or not tanh_out.is_contiguous():
@@ -298,11 +331,20 @@ class MetropolisSampler:
                 a.localop = C.pointer(st)
             else:
                 raise NotImplementedError(f"no fused local-energy kernel for {type(operator).__name__}")
+        part = None
+        if stats_shift is not None:
+            if operator is None:
+                raise ValueError("stats_shift needs an operator")
+            part = torch.empty(_lib.NK_STATS_NPARTIAL + 1, dtype=torch.float64, device=dev)
+            part[_lib.NK_STATS_NPARTIAL] = float(B)
+            a.stats_out, a.stats_shift = part.data_ptr(), float(stats_shift)
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().nk_sweep(_lib.stream_ptr(dev), C.byref(rbm), C.byref(chains), C.byref(a)))
         n_steps = (n_discard + chain_length) * self.sweep_size
         new_state = state.replace(σ=sigma, rng=(seed, int(chains.t)), log_prob=log_prob, n_accepted_proc=nacc,
                                   n_steps_proc=state.n_steps_proc + n_steps * B)
+        if part is not None:
+            return samples, logp, eloc, new_state, part
         return samples, logp, eloc, new_state
 
     def sample(self, machine, parameters, *, state=None, chain_length=1, return_log_probabilities=False,
@@ -341,6 +383,6 @@ def MetropolisLocal(hilbert, **kwargs):
     return MetropolisSampler(hilbert, LocalRule(), **kwargs)
 
 
-def MetropolisExchange(hilbert, *, clusters=None, graph=None, d_max=1, **kwargs):
+def MetropolisExchange(hilbert, *, clusters=None, graph=None, d_max=1, probabilities=None, **kwargs):
     """``nk.sampler.MetropolisExchange`` (metropolis.py:573-683)."""
-    return MetropolisSampler(hilbert, ExchangeRule(clusters=clusters, graph=graph, d_max=d_max), **kwargs)
+    return MetropolisSampler(hilbert, ExchangeRule(clusters=clusters, graph=graph, d_max=d_max, probabilities=probabilities), **kwargs)

@@ -17,20 +17,61 @@ def _np(t):
     return t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
 
 
+def _gather_chains(t):
+    """This rank's chain shard -> the global array (chains of rank 0, rank 1, ...): the reference serialises the global
+    ``(n_chains, ...)`` arrays (its fields are sharded jax arrays, netket/sampler/metropolis.py:50-74).  Collective."""
+    from .utils import world
+
+    _, ws = world()
+    if ws == 1:
+        return _np(t)
+    import torch.distributed as dist
+
+    src = t.detach()
+    if dist.get_backend() == "gloo":
+        src = src.cpu()
+    parts = [torch.empty_like(src) for _ in range(ws)]
+    dist.all_gather(parts, src.contiguous())
+    return torch.cat(parts, dim=0).cpu().numpy()
+
+
 def sampler_state_to_state_dict(state):
-    return {"σ": _np(state.σ), "rng": np.asarray(state.rng, dtype=np.uint64), "n_steps_proc": np.asarray(state.n_steps_proc, dtype=np.int64),
-            "n_accepted_proc": _np(state.n_accepted_proc)}
+    """Keys and shapes of the reference's state dict: global ``σ (n_chains, N)`` and ``n_accepted_proc (n_chains,)``, the
+    per-process step counter, ``rule_state`` (None for LocalRule / ExchangeRule), no ``log_prob`` (derived)."""
+    return {"σ": _gather_chains(state.σ), "rng": np.asarray(state.rng, dtype=np.uint64), "rule_state": None,
+            "n_steps_proc": np.asarray(state.n_steps_proc, dtype=np.int64), "n_accepted_proc": _gather_chains(state.n_accepted_proc)}
 
 
 def sampler_state_from_state_dict(target, d):
-    """Restore into ``target`` (a freshly initialised state of the sampler that will be used): relaxed, ignore errors."""
+    """Restore into ``target`` (a freshly initialised state of the sampler that will be used): relaxed, ignore errors.
+    A global array is sliced to this rank's chains ``[rank * B, (rank + 1) * B)``; a field whose (global) shape does not
+    fit keeps the target's value and a warning says so."""
+    import warnings
+
+    from .utils import world
+
+    rank, ws = world()
     upd = {}
     dev = target.σ.device
-    if "σ" in d and tuple(np.shape(d["σ"])) == tuple(target.σ.shape):
-        upd["σ"] = torch.as_tensor(np.asarray(d["σ"], dtype=np.int8), device=dev)
-        if "n_accepted_proc" in d and tuple(np.shape(d["n_accepted_proc"])) == tuple(target.n_accepted_proc.shape):
-            upd["n_accepted_proc"] = torch.as_tensor(np.asarray(d["n_accepted_proc"], dtype=np.int64), device=dev)
-            upd["n_steps_proc"] = int(np.asarray(d.get("n_steps_proc", 0)))
+    B, N = target.σ.shape
+
+    def shard(name, arr, trailing):
+        arr = np.asarray(arr)
+        if tuple(arr.shape) == (B * ws,) + trailing:
+            return arr[rank * B:(rank + 1) * B]
+        warnings.warn(f"sampler state: stored {name} of shape {tuple(arr.shape)} does not fit {(B * ws,) + trailing}; "
+                      "keeping the freshly initialised value", UserWarning, stacklevel=3)
+        return None
+
+    if "σ" in d:
+        sg = shard("σ", d["σ"], (N,))
+        if sg is not None:
+            upd["σ"] = torch.as_tensor(np.ascontiguousarray(sg.astype(np.int8)), device=dev)
+            if "n_accepted_proc" in d:
+                na = shard("n_accepted_proc", d["n_accepted_proc"], ())
+                if na is not None:
+                    upd["n_accepted_proc"] = torch.as_tensor(np.ascontiguousarray(na.astype(np.int64)), device=dev)
+                    upd["n_steps_proc"] = int(np.asarray(d.get("n_steps_proc", 0)))
     if "rng" in d and np.size(d["rng"]) == 2:
         r = np.asarray(d["rng"], dtype=np.uint64).reshape(2)
         upd["rng"] = (int(r[0]), int(r[1]))

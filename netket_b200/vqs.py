@@ -22,6 +22,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from ._dispatch import Dispatcher
 from .models import RBM
 from .operator import IsingJax, LocalOperatorJax
 from .stats import Stats, statistics
@@ -55,6 +56,71 @@ class LocalEstimators:
         return tuple(self.data.shape)
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# Seam S4: the local-estimator multimethods (netket/vqs/mc/common.py:31-99; registrations of mc_state/expect.py:54-78,
+# 124-128, local_estimators.py:41-82).  `MCState.local_estimators / expect` go through them, so a user overload
+#     @nk.vqs.local_estimators.dispatch
+#     def _(vstate: nk.vqs.MCState, op: MyOperator, chunk_size: None): ...
+# takes effect exactly as in the reference (docs/advanced/custom-operators/local-estimators.ipynb).
+# ------------------------------------------------------------------------------------------------------------------
+get_local_kernel_arguments = Dispatcher(
+    "get_local_kernel_arguments", "(vstate, O) -> (sigma, args): the samples and whatever the local kernel needs (common.py:31-46)")
+get_local_kernel = Dispatcher(
+    "get_local_kernel", "(vstate, O[, chunk_size]) -> kernel(logpsi, pars, sigma, args[, chunk_size=]) -> O_loc[B] (common.py:49-67)")
+local_estimators = Dispatcher(
+    "local_estimators", "(vstate, O, chunk_size) -> LocalEstimators with data (n_chains, chain_length) (common.py:70-99)")
+expect = Dispatcher("expect", "(vstate, O, chunk_size) -> Stats (mc_state/expect.py:124-128)")
+
+
+def check_hilbert(A, B):
+    """common.py:24-28."""
+    if not A == B:
+        raise NotImplementedError(f"Non matching hilbert spaces {A} and {B}")
+
+
+def local_value_kernel_rbm(logpsi, pars, sigma, op, *, chunk_size=None):
+    """``local_value_kernel_jax`` (netket/vqs/mc/kernels.py:62-71) for (RBM, Ising | LocalOperator): O_loc[...] of sigma[..., N]
+    from nk_eloc_ising_rbm / nk_eloc_localop_rbm - sigma' is never materialised.  ``logpsi``: the RBM module or its bound
+    ``apply``; any other ansatz raises (there is no generic / CPU path).  ``chunk_size`` is accepted and ignored."""
+    model = getattr(logpsi, "__self__", logpsi)
+    if not isinstance(model, RBM):
+        raise NotImplementedError(f"{type(model).__name__}: the fused local-value kernel recognises netket_b200.models.RBM only")
+    return _eloc_on_samples(pars, op, sigma)
+
+
+def _eloc_on_samples(variables, op, sigma, path=_lib.NK_PATH_AUTO, ws_holder=None):
+    """Stand-alone E_loc on sigma[..., N] (any leading dimensions)."""
+    rbm = RBM.c_struct(variables)
+    W, _, _ = RBM.unpack(variables)
+    dev = W.device
+    shape = tuple(sigma.shape[:-1])
+    s8 = sigma.reshape(-1, rbm.N).to(torch.int8).contiguous()
+    B = s8.shape[0]
+    out_dtype = torch.promote_types(_lib.torch_dtype(op.dtype), W.dtype)
+    out = torch.empty((B,), dtype=out_dtype, device=dev)
+    st = op._c_struct(dev)
+    ws = None
+    if path != _lib.NK_PATH_GENERIC:  # scratch of the product-form kernel (theta + tables), cached per size
+        nbytes = int(_lib.lib().nk_sweep_workspace_bytes(C.byref(rbm), B))
+        if nbytes > 0:
+            holder = ws_holder if ws_holder is not None else _eloc_on_samples.__dict__
+            cur = holder.get("_eloc_ws")
+            if cur is None or cur.numel() < nbytes or cur.device != dev:
+                cur = holder["_eloc_ws"] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            ws = cur
+    wsp = _lib.ptr(ws) if ws is not None else None
+    with torch.cuda.device(dev):
+        if isinstance(op, IsingJax):
+            _lib.check(_lib.lib().nk_eloc_ising_rbm(_lib.stream_ptr(dev), C.byref(rbm), C.byref(st), _lib.ptr(s8), B,
+                                                    _lib.ptr(out), _lib.dtype_code(out_dtype), path, wsp))
+        elif isinstance(op, LocalOperatorJax):
+            _lib.check(_lib.lib().nk_eloc_localop_rbm(_lib.stream_ptr(dev), C.byref(rbm), C.byref(st), _lib.ptr(s8), B,
+                                                      _lib.ptr(out), _lib.dtype_code(out_dtype), path, wsp))
+        else:
+            raise NotImplementedError(f"no local-value kernel for {type(op).__name__}")
+    return out.reshape(shape)
+
+
 class MCState:
     def __init__(self, sampler, model=None, *, n_samples=None, n_samples_per_rank=None, n_discard_per_chain=None,
                  chunk_size=None, variables=None, seed=None, sampler_seed=None):
@@ -71,7 +137,9 @@ class MCState:
         self._variables = variables
         self.sampler_state = sampler.init_state(model, variables, seed=self._sampler_seed)
         self._samples = None
-        self._eloc_cache = {}
+        self._eloc_cache = None   # (operator, E_loc): the operator object itself is held, an id() can be recycled
+        self._stats_cache = None  # (operator, Stats) of the fused launch
+        self._shift_hint = None   # (operator, last mean): shift of the in-kernel statistics (any estimate is exact)
         self._eloc_ws = None
         self._forces_ws = None
         self._sampler_state_previous = None
@@ -181,10 +249,11 @@ class MCState:
     def reset(self):
         """Drop the cached samples so that the next access re-samples (state.py:514-519)."""
         self._samples = None
-        self._eloc_cache = {}
+        self._eloc_cache = None
+        self._stats_cache = None
         self._tanh = None
 
-    def _run(self, chain_length, n_discard, operator=None, path=_lib.NK_PATH_AUTO, want_tanh=False):
+    def _run(self, chain_length, n_discard, operator=None, path=_lib.NK_PATH_AUTO, want_tanh=False, fused_stats=False):
         sa = self._sampler
         # sampler.reset: counters zeroed (and chains re-randomised if reset_chains); log_prob is rebuilt in-kernel
         st = self.sampler_state.replace(n_steps_proc=0, n_accepted_proc=torch.zeros_like(self.sampler_state.n_accepted_proc))
@@ -195,19 +264,44 @@ class MCState:
         if want_tanh:  # tanh(theta) of every sample, written by the sweep kernel for the forces (1.7 GB at 2^20 x 400 fp32)
             W, _, _ = RBM.unpack(self._variables)
             self._tanh = torch.empty((sa.n_chains_per_rank, chain_length, W.shape[1]), dtype=W.dtype, device=W.device)
-        samples, _, eloc, st = sa._launch(self._model, self._variables, st, chain_length, n_discard=n_discard,
-                                          operator=operator, path=path, tanh_out=self._tanh)
+        shift = None
+        if fused_stats and operator is not None:
+            hint = self._shift_hint
+            shift = hint[1] if (hint is not None and hint[0] is operator) else 0.0
+        out = sa._launch(self._model, self._variables, st, chain_length, n_discard=n_discard, operator=operator, path=path,
+                         tanh_out=self._tanh, stats_shift=shift)
+        samples, _, eloc, st = out[:4]
         self.sampler_state = st
+        if shift is not None:
+            self._stats_cache = (operator, self._finish_stats(eloc, out[4], shift, chain_length))
+            self._shift_hint = (operator, self._stats_cache[1].mean)
         return samples, eloc
+
+    def _finish_stats(self, eloc, part, shift, L):
+        """ONE all-reduce (NK_STATS_NPARTIAL sums + the chain count) and ONE host read per fused expect.  The sums are shifted
+        by `shift`; if that estimate turns out to be so far from the mean that the one-pass variance formulas would lose
+        more than ~1e-11 to cancellation (first call on a low-variance state), the two-pass kernel runs instead."""
+        from .stats import _allreduce, finalize
+
+        _allreduce(part)
+        p = part.tolist()
+        n_chains_total = int(round(p[_lib.NK_STATS_NPARTIAL]))
+        sums = p[:_lib.NK_STATS_NPARTIAL]
+        ts = float(n_chains_total * L)
+        dm = sums[7] / ts
+        var = sums[0] / ts - dm * dm
+        if not (dm * dm * max(L, 1) <= 1.0e5 * var):
+            return statistics(eloc)
+        return finalize(sums, shift, n_chains_total, L)
 
     def sample(self, *, chain_length=None, n_samples=None, n_discard_per_chain=None):
         """state.py:521-576."""
+        if n_samples is not None and chain_length is not None:
+            raise ValueError("Cannot specify both `chain_length` and `n_samples`.")  # state.py:540-546
         if n_samples is None and chain_length is None:
             chain_length = self._chain_length
-        else:
-            if chain_length is None:
-                chain_length = compute_chain_length(self._sampler.n_chains, n_samples)
-            self._chain_length = chain_length
+        elif chain_length is None:
+            chain_length = compute_chain_length(self._sampler.n_chains, n_samples)
         if n_discard_per_chain is None:
             n_discard_per_chain = self._n_discard
         self.reset()
@@ -235,48 +329,30 @@ class MCState:
 
     def _eloc_on_samples(self, op, sigma, path=_lib.NK_PATH_AUTO):
         """Stand-alone E_loc on sigma[..., N]."""
-        rbm = RBM.c_struct(self._variables)
-        W, _, _ = RBM.unpack(self._variables)
-        dev = W.device
-        shape = tuple(sigma.shape[:-1])
-        s8 = sigma.reshape(-1, rbm.N).to(torch.int8).contiguous()
-        B = s8.shape[0]
-        out_dtype = torch.promote_types(_lib.torch_dtype(op.dtype), W.dtype)
-        out = torch.empty((B,), dtype=out_dtype, device=dev)
-        st = op._c_struct(dev)
-        ws = None
-        if path != _lib.NK_PATH_GENERIC:  # scratch of the product-form kernel (theta + tables), cached per size
-            nbytes = int(_lib.lib().nk_sweep_workspace_bytes(C.byref(rbm), B))
-            if nbytes > 0:
-                if self._eloc_ws is None or self._eloc_ws.numel() < nbytes or self._eloc_ws.device != dev:
-                    self._eloc_ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-                ws = self._eloc_ws
-        wsp = _lib.ptr(ws) if ws is not None else None
-        with torch.cuda.device(dev):
-            if isinstance(op, IsingJax):
-                _lib.check(_lib.lib().nk_eloc_ising_rbm(_lib.stream_ptr(dev), C.byref(rbm), C.byref(st), _lib.ptr(s8), B,
-                                                        _lib.ptr(out), _lib.dtype_code(out_dtype), path, wsp))
-            else:
-                _lib.check(_lib.lib().nk_eloc_localop_rbm(_lib.stream_ptr(dev), C.byref(rbm), C.byref(st), _lib.ptr(s8), B,
-                                                          _lib.ptr(out), _lib.dtype_code(out_dtype), path, wsp))
-        return out.reshape(shape)
+        return _eloc_on_samples(self._variables, op, sigma, path, self.__dict__)
 
     def local_estimators(self, op, *, chunk_size=None):
-        """O_loc for every sample, shape (n_chains_per_rank, chain_length) (state.py:612-692)."""
-        self._check_operator(op)
-        key = id(op)
-        if key in self._eloc_cache:
-            return self._eloc_cache[key]
-        if self._samples is None:
-            self._samples, eloc = self._run(self._chain_length, self._n_discard, operator=op)
-        else:
-            eloc = self._eloc_on_samples(op, self._samples)
-        self._eloc_cache = {key: eloc}
-        return eloc
+        """O_loc for every sample, shape (n_chains_per_rank, chain_length) (state.py:612-692): the `local_estimators`
+        multimethod on (type(self), type(op), chunk_size), `.data` of its result."""
+        return local_estimators(self, op, self.chunk_size if chunk_size is None else chunk_size).data
 
     def expect(self, op):
-        """<O> with MC statistics (state.py:695-712)."""
-        return statistics(self.local_estimators(op))
+        """<O> with MC statistics (state.py:695-712): the `expect` multimethod.  For the built-in operators and no cached
+        samples this is ONE launch: sweeps, local energies and the statistics' partial sums come out of the same kernel,
+        followed by one all-reduce and one host read."""
+        return expect(self, op, self.chunk_size)
+
+    def _local_estimators_fused(self, op):
+        """Built-in operators: cached E_loc, else the fused launch (no samples yet), else the stand-alone kernel."""
+        self._check_operator(op)
+        if self._eloc_cache is not None and self._eloc_cache[0] is op:
+            return self._eloc_cache[1]
+        if self._samples is None:
+            self._samples, eloc = self._run(self._chain_length, self._n_discard, operator=op, fused_stats=True)
+        else:
+            eloc = self._eloc_on_samples(op, self._samples)
+        self._eloc_cache = (op, eloc)
+        return eloc
 
     # ------------------------------------------------------------------ streaming callers (SURVEY.md §8f rank 2)
     def _sample_and_estimate(self, op, n_discard_per_chain=None):
@@ -285,7 +361,7 @@ class MCState:
         self.reset()
         n_discard = self._n_discard if n_discard_per_chain is None else n_discard_per_chain
         self._samples, eloc = self._run(self._chain_length, n_discard, operator=op)
-        self._eloc_cache = {id(op): eloc}
+        self._eloc_cache = (op, eloc)
         return eloc
 
     def _set_sampler_keep_state(self, sampler, sampler_state):
@@ -334,10 +410,10 @@ class MCState:
 
         self._check_operator(op)
         if self._samples is None:  # one fused launch: sweeps + E_loc + tanh(theta) of every sample
-            self._samples, eloc = self._run(self._chain_length, self._n_discard, operator=op, want_tanh=True)
-            self._eloc_cache = {id(op): eloc}
+            self._samples, eloc = self._run(self._chain_length, self._n_discard, operator=op, want_tanh=True, fused_stats=True)
+            self._eloc_cache = (op, eloc)
+        stats = self.expect(op)
         eloc = self.local_estimators(op)
-        stats = statistics(eloc)
         samples = self.samples
         rbm = RBM.c_struct(self._variables)
         W, b, a = RBM.unpack(self._variables)
@@ -387,3 +463,63 @@ class MCState:
         return (f"MCState(\n  hilbert = {self.hilbert},\n  sampler = {self._sampler},\n  n_samples = {self.n_samples},\n"
                 f"  n_discard_per_chain = {self._n_discard},\n  sampler_state = {self.sampler_state},\n"
                 f"  n_parameters = {self.n_parameters})")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# registrations for (MCState, Ising | LocalOperator) - mc_state/expect.py:54-78,124-128; local_estimators.py:41-82
+# ------------------------------------------------------------------------------------------------------------------
+_BUILTIN_OPS = (IsingJax, LocalOperatorJax)
+
+
+@get_local_kernel_arguments.dispatch
+def _(vstate: MCState, op: _BUILTIN_OPS):
+    check_hilbert(vstate.hilbert, op.hilbert)
+    return vstate.samples, op  # a DiscreteJaxOperator is its own kernel argument (expect.py:69-73)
+
+
+@get_local_kernel.dispatch
+def _(vstate: MCState, op: _BUILTIN_OPS):
+    return local_value_kernel_rbm
+
+
+@get_local_kernel.dispatch
+def _(vstate: MCState, op: _BUILTIN_OPS, chunk_size: (int, type(None))):
+    return local_value_kernel_rbm  # nothing is materialised, so there is nothing to chunk
+
+
+@get_local_kernel.dispatch(precedence=-10)
+def _(vstate, op, chunk_size: None):  # common.py:63-67
+    return get_local_kernel(vstate, op)
+
+
+@local_estimators.dispatch
+def _(vstate: MCState, op: _BUILTIN_OPS, chunk_size: (int, type(None))):
+    return LocalEstimators(vstate._local_estimators_fused(op))
+
+
+@local_estimators.dispatch(precedence=-50)
+def _(vstate: MCState, op, chunk_size: (int, type(None))):
+    """Generic route of local_estimators.py:41-82 for operators registered through get_local_kernel(_arguments)."""
+    sigma, args = get_local_kernel_arguments(vstate, op)
+    kernel = get_local_kernel(vstate, op, chunk_size)
+    data = kernel(vstate.model, vstate.variables, sigma.reshape(-1, sigma.shape[-1]), args)
+    return LocalEstimators(data.reshape(sigma.shape[:-1]))
+
+
+@local_estimators.dispatch(precedence=-100)
+def _(vstate, op, chunk_size):  # common.py:84-99
+    raise NotImplementedError(
+        f"local_estimators is not implemented for the combination of vstate type {type(vstate).__name__} and operator type "
+        f"{type(op).__name__}.\nTo add support, register a dispatch. For MCState + custom AbstractOperator, define separate "
+        f"chunk_size=None and chunk_size=int overloads to avoid ambiguity:\n    @nk.vqs.local_estimators.dispatch\n"
+        f"    def _(vstate: YourState, op: YourOp, chunk_size: None):\n        ...\n    @nk.vqs.local_estimators.dispatch\n"
+        f"    def _(vstate: YourState, op: YourOp, chunk_size: int):\n        ...")
+
+
+@expect.dispatch
+def _(vstate: MCState, op, chunk_size: (int, type(None))):  # mc_state/expect.py:124-128
+    le = local_estimators(vstate, op, chunk_size)
+    sc = vstate._stats_cache
+    if sc is not None and sc[0] is op and vstate._eloc_cache is not None and vstate._eloc_cache[1] is le.data:
+        return sc[1]  # reduced inside the sweep kernel
+    return le.to_stats()

@@ -1,6 +1,7 @@
-"""Forces / gradient of <O> for the RBM (TEST INFRASTRUCTURE; parity unpinned against a golden vector: the reference
-obtains them by reverse-mode autodiff, which cannot run here - the closed-form log-derivatives are instead checked against
-finite differences of ``oracle.rbm.logpsi`` in tests/test_oracle.py).
+"""Forces / gradient of <O> for the RBM (TEST INFRASTRUCTURE).  Pinned by tests/golden/sampler_vectors.npz:
+``forces_expect_hermitian`` executed from the reference's source (tests/golden/make_golden_sampler.py; its reverse-mode vjp
+replaced by Richardson-extrapolated central differences of the reference's forward pass), tests/test_golden_sampler.py;
+the closed-form log-derivatives are also checked against finite differences of ``oracle.rbm.logpsi`` in tests/test_oracle.py.
 
 ``forces_expect_hermitian`` (netket/vqs/mc/mc_state/expect_forces.py:69-112):
 
@@ -38,3 +39,13 @@ def forces(samples, eloc, W, b, a, mean=None, n_total=None):
 def grad(samples, eloc, W, b, a, **kw):
     f = forces(samples, eloc, W, b, a, **kw)
     return {k: (None if v is None else 2.0 * v) for k, v in f.items()}
+
+
+def expect_and_forces(samples, conn_fn, W, b, a):
+    """``expect_and_forces`` (expect_forces.py:39-112) on samples[n_chains, chain_length, N]: (mean of E_loc, forces in the
+    parameter layout of the reference: kernel / bias / visible_bias)."""
+    from .estimators import local_estimators
+
+    eloc = local_estimators(samples, conn_fn, W, b, a)
+    f = forces(samples, eloc, W, b, a)
+    return float(eloc.mean()), {"kernel": f["W"], "bias": f["b"], "visible_bias": f["a"]}

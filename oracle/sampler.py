@@ -12,7 +12,10 @@ Rules:
     flip for 2 local states (netket/hilbert/random/homogeneous.py:157-159), no correction.
   * ExchangeRule (netket/sampler/rules/exchange.py:143-184): one *hoppable* cluster
     (sigma_i != sigma_j) chosen uniformly, swap, correction
-    log n_hop(sigma) - log n_hop(sigma').  (``probabilities=None`` only.)
+    log n_hop(sigma) - log n_hop(sigma').  With ``probabilities`` (:86-123,155-160,177-182)
+    the cluster is drawn with weight mask * p by inverse CDF -- JAX's ``random.choice``
+    algorithm, ``searchsorted(cumsum(w), total * r)`` -- at r = (w0 + 1/2) / 2^32, and the
+    correction is log sum_c w_c(sigma) - log sum_c w_c(sigma').
 The per-step randomness comes from the explicit proposal stream of oracle/rng.py (or from
 arrays passed in ``stream=``), never from a hidden generator.
 """
@@ -35,6 +38,27 @@ def _propose_local(sigma, w0):
     rows = np.arange(sigma.shape[0])
     sp[rows, idx] = -sp[rows, idx]
     return sp, None, idx
+
+
+def _propose_exchange_weighted(sigma, w0, clusters, prob):
+    B = sigma.shape[0]
+    mask = hoppable_mask(sigma, clusters)
+    w = mask * prob[None, :]                      # _weighted_mask (exchange.py:155-160)
+    cs = np.cumsum(w, axis=1)
+    tot = cs[:, -1]
+    r = tot * ((np.asarray(w0, dtype=np.float64) + 0.5) * 2.0 ** -32)
+    sel = np.minimum((cs < r[:, None]).sum(axis=1), clusters.shape[0] - 1)   # searchsorted(cumsum, r), side="left"
+    rows = np.arange(B)
+    si, sj = clusters[sel, 0], clusters[sel, 1]
+    sp = sigma.copy()
+    ok = tot > 0
+    sp[rows[ok], si[ok]] = sigma[rows[ok], sj[ok]]
+    sp[rows[ok], sj[ok]] = sigma[rows[ok], si[ok]]
+    tot_p = (hoppable_mask(sp, clusters) * prob[None, :]).sum(axis=1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        corr = np.log(tot) - np.log(tot_p)
+    corr = np.where(ok, corr, np.nan)
+    return sp, corr, sel
 
 
 def _propose_exchange(sigma, w0, clusters):
@@ -82,6 +106,7 @@ def sample_chain(
     clusters=None,
     stream=None,
     return_trace=False,
+    probabilities=None,
 ):
     """Run ``chain_length`` sweeps.  sigma[B,N] int8 (+/-1).  rule in {"local","exchange"}.
 
@@ -115,6 +140,8 @@ def sample_chain(
         for _ in range(sweep_size):
             if rule == "local":
                 sp, corr, sel = _propose_local(sigma, w0[t])
+            elif rule == "exchange" and probabilities is not None:
+                sp, corr, sel = _propose_exchange_weighted(sigma, w0[t], clusters, np.asarray(probabilities, dtype=np.float64))
             elif rule == "exchange":
                 sp, corr, sel = _propose_exchange(sigma, w0[t], clusters)
             else:

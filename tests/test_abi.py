@@ -140,8 +140,8 @@ def test_stats_finalize_matches_oracle(lib_built, shape):
     rs = np.random.default_rng(0)
     x = rs.normal(size=shape).cumsum(axis=1) * 0.2 + rs.normal(size=shape) - 7.0
     mean = x.mean()
-    for shift in (mean, mean + 0.37):  # any shift gives the same statistics
-        st = nkstats.finalize(_partials(x, shift), mean, shape[0], shape[1])
+    for shift in (mean, mean + 0.37, 0.0):  # any shift gives the same statistics (the one-pass, in-kernel reduction uses an estimate)
+        st = nkstats.finalize(_partials(x, shift), shift, shape[0], shape[1])
         ref = oracle.stats.statistics(x)
         for k in ("mean", "variance", "error_of_mean", "tau_corr", "R_hat"):
             np.testing.assert_allclose(getattr(st, k), ref[k], rtol=1e-9, atol=1e-12, equal_nan=True, err_msg=k)

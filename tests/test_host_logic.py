@@ -142,8 +142,15 @@ def test_sampler_construction_rules():
     assert np.array_equal(ex.rule.clusters, ograph.compute_clusters(8, np.asarray(g.edges()), 2)) and len(ex.rule.clusters) == 16
     with pytest.raises(ValueError):
         nk.sampler.MetropolisExchange(hi)
-    with pytest.raises(NotImplementedError):
-        nk.sampler.ExchangeRule(graph=g, probabilities=[1.0])
+    # ExchangeRule(probabilities=...): one weight per graph distance, or per cluster (rules/exchange.py:86-123,200-203)
+    wr = nk.sampler.ExchangeRule(graph=g, d_max=2, probabilities=[0.7, 0.3])
+    D = np.asarray(g.distances())
+    assert np.array_equal(wr.probabilities, np.array([0.7, 0.3])[D[wr.clusters[:, 0], wr.clusters[:, 1]] - 1])
+    assert nk.sampler.MetropolisExchange(hi, clusters=[(0, 1), (2, 5)], probabilities=[1.0, 2.0]).rule.probabilities.tolist() == [1.0, 2.0]
+    with pytest.raises(ValueError, match="positive"):
+        nk.sampler.ExchangeRule(graph=g, probabilities=[0.0])
+    with pytest.raises(TypeError, match="don't match"):
+        nk.sampler.ExchangeRule(clusters=[(0, 1), (2, 5)], probabilities=[1.0])
     assert "MetropolisSampler" in repr(sa) and "ExchangeRule(# of clusters: 16)" in repr(ex)
 
 
