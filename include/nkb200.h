@@ -259,16 +259,54 @@ int nk_rbm_jvp(void *stream, const nk_rbm_t *v, const int8_t *samples, int64_t N
 
 /* ---------------------------------------------------------------------------------------------
  * Host-buffer API: one VMC inner-loop step with HOST pointers (what bench.py's `e2e` times).
- * The context owns the device buffers (parameters, chains, operator tables, E_loc).
+ * The context owns the device buffers (parameters, chains, operator tables, E_loc, samples).
  * Mirrors   vs.parameters = ...; vs.reset(); vs.expect(H)   of
- * netket/vqs/mc/mc_state/state.py:514-576,695-712 for (MetropolisLocal, RBM, Ising).
+ * netket/vqs/mc/mc_state/state.py:514-576,695-712 for (MetropolisLocal | MetropolisExchange, RBM, Ising | LocalOperator).
+ *
+ * A step is two calls, so that the caller's own collective can run between them on multi-GPU jobs:
+ *   nk_ctx_step_begin   upload W, b, a; run n_discard + chain_length sweeps fused with E_loc and with the statistics'
+ *                       partial sums; asynchronous on nk_ctx_stream(ctx);
+ *   (all-reduce nk_ctx_partials_device(ctx), NK_CTX_NPARTIAL doubles, in place, ordered after nk_ctx_stream(ctx):
+ *    NCCL / torch.distributed / jax.lax.psum - the library itself never communicates)
+ *   nk_ctx_step_end     copy E_loc (and the samples) to the host, ONE synchronisation, the five statistics + acceptance.
+ * nk_ctx_step_host = begin + end for a single device.
  * ------------------------------------------------------------------------------------------- */
 typedef struct nk_ctx nk_ctx;
+#define NK_CTX_NPARTIAL (NK_STATS_NPARTIAL + 2) /* [phase-1 sums | number of chains | sum of the acceptance counters] */
+#define NK_RESHIFT 1 /* nk_ctx_step_end (multi-device only): the statistics' shift (previous mean) was too far from this
+                        step's mean for full precision; results are valid to ~1e-8, the next step re-centres */
+typedef struct nk_ctx_desc_t {
+  int32_t device, N, M, dtype;
+  int64_t n_chains;      /* chains on this device */
+  int32_t chain_length;  /* recorded sweeps per step */
+  int32_t sweep_size;    /* 0 => N (metropolis.py:283-284) */
+  int32_t rule;          /* NK_RULE_* */
+  int32_t n_clusters;
+  const int32_t *clusters_host;     /* [n_clusters, 2]   (ExchangeRule) */
+  const double *cluster_probs_host; /* [n_clusters] or NULL (ExchangeRule(probabilities=)) */
+  double machine_pow;               /* default 2 */
+  int32_t n_down;                   /* initial configurations: < 0 unconstrained, else exactly n_down spins down (total_sz) */
+  int32_t return_samples;           /* keep the samples [n_chains, chain_length, N] of every step for nk_ctx_step_end */
+  const nk_ising_t *ising_host;     /* exactly one of the two operators; every pointer inside is a HOST pointer */
+  const nk_localop_t *localop_host;
+  uint64_t seed, chain_offset;
+  void *stream;                     /* cudaStream_t the context enqueues on, or NULL: a stream of its own */
+  int32_t eloc_in_param_dtype;      /* 0: E_loc in promote(operator, parameter) = float64; 1: in the parameter dtype */
+  int32_t reserved;
+} nk_ctx_desc_t;
+int nk_ctx_create2(nk_ctx **out, const nk_ctx_desc_t *desc);
+/* (MetropolisLocal, Ising, machine_pow 2, E_loc in the parameter dtype): the v1 signature, kept */
 int nk_ctx_create(nk_ctx **out, int32_t device, int32_t N, int32_t M, int32_t dtype, int64_t n_chains, int32_t chain_length,
                   const int32_t *edges_host, int32_t n_edges, double h, double J, uint64_t seed, uint64_t chain_offset);
 void nk_ctx_destroy(nk_ctx *ctx);
+void *nk_ctx_stream(nk_ctx *ctx);
+double *nk_ctx_partials_device(nk_ctx *ctx);
+int nk_ctx_step_begin(nk_ctx *ctx, const void *W_host, const void *b_host, const void *a_host, int32_t n_discard);
+/* eloc_host [n_chains, chain_length] (float64, or the parameter dtype); samples_host [n_chains, chain_length, N] or NULL;
+ * stats_host [6]: mean, error_of_mean, variance, tau_corr, R_hat, acceptance - over ALL devices if the partials were reduced */
+int nk_ctx_step_end(nk_ctx *ctx, void *eloc_host, int8_t *samples_host, double *stats_host);
 /* upload parameters (pinned or pageable host memory), run n_discard + chain_length sweeps fused with E_loc,
- * copy E_loc [n_chains, chain_length] (dtype) and the 5 statistics + acceptance back to host; synchronises. */
+ * copy E_loc [n_chains, chain_length] and the 5 statistics + acceptance back to host; synchronises once. */
 int nk_ctx_step_host(nk_ctx *ctx, const void *W_host, const void *b_host, const void *a_host, int32_t n_discard,
                      void *eloc_host, double *stats_host /* [6]: mean, err, var, tau, rhat, acceptance */);
 /* copy the current configurations sigma [n_chains, N] to host */

@@ -65,6 +65,18 @@ class nk_sweep_t(C.Structure):
                 ("stats_out", C.c_void_p), ("stats_shift", C.c_double), ("cluster_probs", C.c_void_p)]
 
 
+class nk_ctx_desc_t(C.Structure):
+    _fields_ = [("device", C.c_int32), ("N", C.c_int32), ("M", C.c_int32), ("dtype", C.c_int32), ("n_chains", C.c_int64),
+                ("chain_length", C.c_int32), ("sweep_size", C.c_int32), ("rule", C.c_int32), ("n_clusters", C.c_int32),
+                ("clusters_host", C.c_void_p), ("cluster_probs_host", C.c_void_p), ("machine_pow", C.c_double),
+                ("n_down", C.c_int32), ("return_samples", C.c_int32), ("ising_host", C.POINTER(nk_ising_t)),
+                ("localop_host", C.POINTER(nk_localop_t)), ("seed", C.c_uint64), ("chain_offset", C.c_uint64), ("stream", C.c_void_p),
+                ("eloc_in_param_dtype", C.c_int32), ("reserved", C.c_int32)]
+
+
+NK_CTX_NPARTIAL = NK_STATS_NPARTIAL + 2
+NK_RESHIFT = 1
+
 # every symbol include/nkb200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "nk_last_error": (C.c_char_p, []),
@@ -101,7 +113,12 @@ SYMBOLS = {
                                            C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "nk_ctx_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32,
                                 C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_uint64, C.c_uint64]),
+    "nk_ctx_create2": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(nk_ctx_desc_t)]),
     "nk_ctx_destroy": (None, [C.c_void_p]),
+    "nk_ctx_stream": (C.c_void_p, [C.c_void_p]),
+    "nk_ctx_partials_device": (C.c_void_p, [C.c_void_p]),
+    "nk_ctx_step_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "nk_ctx_step_end": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
     "nk_ctx_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                    C.POINTER(C.c_double)]),
     "nk_ctx_get_sigma_host": (C.c_int, [C.c_void_p, C.c_void_p]),

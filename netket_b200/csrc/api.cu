@@ -459,31 +459,178 @@ int nk_stats_finalize(const double *sums_host, double mean, int64_t n_chains_tot
 // ------------------------------------------------------------------------------------------ host-buffer context
 struct nk_ctx {
   int device;
-  int32_t N, M, dtype, chain_length, n_edges;
+  int32_t N, M, dtype, chain_length, sweep_size, rule, n_clusters, n_down, return_samples, op_kind;  // op_kind 1 ising, 2 localop
   int64_t B;
-  size_t esz;
+  size_t esz, eloc_esz;
+  int32_t eloc_dtype;
+  double machine_pow;
   cudaStream_t stream;
+  bool own_stream;
   void *W, *b, *a;
-  int8_t *sigma;
+  int8_t *sigma, *samples;
   void *log_prob;
   int64_t *n_accepted;
-  int32_t *edges;
+  int32_t *edges, *clusters;
+  double *cluster_probs;
   void *eloc;
-  double *partials;       // device, NK_STATS_NPARTIAL
+  double *partials;       // device, NK_CTX_NPARTIAL: [NK_STATS_NPARTIAL sums | n_chains | n_accepted]
   double *partials_host;  // pinned
-  int64_t *nacc_host;     // pinned, 1
-  int64_t *nacc_sum;      // device, 1
   void *workspace;        // nk_sweep_workspace_bytes (theta scratch + hand-over flag)
   nk_ising_t ising;
+  nk_localop_t localop;
+  std::vector<void *> op_allocs;
   uint64_t seed, t, chain_offset;
+  double shift;           // shift of the in-kernel statistics: the previous step's mean
+  int32_t n_discard_last;
+  bool has_b, has_a;
 };
 
-__global__ void acc_sum_kernel(const int64_t *x, int64_t n, unsigned long long *out) {
+__global__ void ctx_tail_kernel(const int64_t *nacc, int64_t n, double *partials) {
+  // partials[NPARTIAL] = n_chains, partials[NPARTIAL + 1] = sum of the acceptance counters (exact in double below 2^53)
   unsigned long long s = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    s += (unsigned long long)x[i];
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += (unsigned long long)nacc[i];
   for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
-  if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+  __shared__ unsigned long long sh[32];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+    partials[NK_STATS_NPARTIAL] = (double)n;
+    partials[NK_STATS_NPARTIAL + 1] = (double)t;
+  }
+}
+
+}  // extern "C"
+
+template <typename T>
+static int upload(void **dst, const T *src_host, size_t count, cudaStream_t st, std::vector<void *> *owned) {
+  *dst = nullptr;
+  if (count == 0 || src_host == nullptr) return NK_OK;
+  NK_CUDA_OK(cudaMalloc(dst, count * sizeof(T)));
+  if (owned) owned->push_back(*dst);
+  NK_CUDA_OK(cudaMemcpyAsync(*dst, src_host, count * sizeof(T), cudaMemcpyHostToDevice, st));
+  return NK_OK;
+}
+
+extern "C" {
+
+int nk_ctx_create2(nk_ctx **out, const nk_ctx_desc_t *d) {
+  NK_CHECK_ARG(out != nullptr && d != nullptr, "nk_ctx_create2: NULL argument");
+  NK_CHECK_ARG(d->N > 0 && d->M > 0 && d->n_chains > 0 && d->chain_length > 0, "nk_ctx_create2: bad sizes");
+  NK_CHECK_ARG(d->dtype == NK_F32 || d->dtype == NK_F64, "nk_ctx_create2: bad dtype");
+  NK_CHECK_ARG(d->rule == NK_RULE_LOCAL || d->rule == NK_RULE_EXCHANGE, "nk_ctx_create2: unknown rule %d", d->rule);
+  NK_CHECK_ARG(d->rule != NK_RULE_EXCHANGE || (d->clusters_host != nullptr && d->n_clusters > 0), "nk_ctx_create2: ExchangeRule needs clusters");
+  NK_CHECK_ARG(d->machine_pow >= 0.0, "nk_ctx_create2: machine_pow must be a non-negative real");
+  NK_CHECK_ARG(d->sweep_size >= 0, "nk_ctx_create2: bad sweep_size");
+  NK_CHECK_ARG((d->ising_host != nullptr) != (d->localop_host != nullptr), "nk_ctx_create2: pass exactly one operator (ising_host / localop_host)");
+  NK_CHECK_ARG(d->n_down <= d->N, "nk_ctx_create2: n_down > N");
+  if (d->ising_host) NK_CHECK_ARG(d->ising_host->n_edges >= 0 && (d->ising_host->n_edges == 0 || d->ising_host->edges), "nk_ctx_create2: bad edges");
+  if (d->localop_host) {
+    int rc = check_localop(d->localop_host, d->N, "nk_ctx_create2");
+    if (rc) return rc;
+  }
+  NK_CUDA_OK(cudaSetDevice(d->device));
+  nk_ctx *c = new nk_ctx();
+  c->device = d->device;
+  c->N = d->N;
+  c->M = d->M;
+  c->dtype = d->dtype;
+  c->B = d->n_chains;
+  c->chain_length = d->chain_length;
+  c->sweep_size = d->sweep_size > 0 ? d->sweep_size : d->N;
+  c->rule = d->rule;
+  c->n_clusters = d->rule == NK_RULE_EXCHANGE ? d->n_clusters : 0;
+  c->n_down = d->n_down;
+  c->return_samples = d->return_samples;
+  c->machine_pow = d->machine_pow;
+  c->esz = d->dtype == NK_F32 ? 4 : 8;
+  c->seed = d->seed;
+  c->t = 0;
+  c->chain_offset = d->chain_offset;
+  c->shift = 0.0;
+  c->n_discard_last = 0;
+  c->W = c->b = c->a = nullptr;
+  c->sigma = c->samples = nullptr;
+  c->log_prob = c->eloc = c->workspace = nullptr;
+  c->n_accepted = nullptr;
+  c->edges = c->clusters = nullptr;
+  c->cluster_probs = nullptr;
+  c->partials = c->partials_host = nullptr;
+  if (d->stream != nullptr) {
+    c->stream = (cudaStream_t)d->stream;
+    c->own_stream = false;
+  } else {
+    NK_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+  }
+  const int64_t B = c->B;
+  const int N = c->N, M = c->M;
+  NK_CUDA_OK(cudaMalloc(&c->W, (size_t)N * M * c->esz));
+  NK_CUDA_OK(cudaMalloc(&c->b, (size_t)M * c->esz));
+  NK_CUDA_OK(cudaMalloc(&c->a, (size_t)N * c->esz));
+  NK_CUDA_OK(cudaMalloc((void **)&c->sigma, (size_t)B * N));
+  NK_CUDA_OK(cudaMalloc(&c->log_prob, (size_t)B * c->esz));
+  NK_CUDA_OK(cudaMalloc((void **)&c->n_accepted, (size_t)B * 8));
+  NK_CUDA_OK(cudaMalloc((void **)&c->partials, sizeof(double) * NK_CTX_NPARTIAL));
+  NK_CUDA_OK(cudaMallocHost((void **)&c->partials_host, sizeof(double) * NK_CTX_NPARTIAL));
+  if (c->return_samples) NK_CUDA_OK(cudaMalloc((void **)&c->samples, (size_t)B * c->chain_length * N));
+  // operator tables: host -> device
+  int rc = NK_OK;
+  if (d->ising_host) {
+    c->op_kind = 1;
+    c->ising = *d->ising_host;
+    void *p = nullptr;
+    rc = upload<int32_t>(&p, d->ising_host->edges, (size_t)2 * d->ising_host->n_edges, c->stream, &c->op_allocs);
+    if (rc) return rc;
+    c->ising.edges = (const int32_t *)p;
+    c->eloc_dtype = NK_F64;  // operator dtype float64 (netket/operator/_ising/base.py:75): E_loc promotes to double ...
+  } else {
+    c->op_kind = 2;
+    c->localop = *d->localop_host;
+    for (int g = 0; g < c->localop.n_groups; ++g) {
+      const nk_localop_group_t &h = d->localop_host->groups[g];
+      nk_localop_group_t &G = c->localop.groups[g];
+      const size_t rows = (size_t)h.n_ops << h.n_sites;
+      void *p = nullptr;
+      if ((rc = upload<int32_t>(&p, h.acting_on, (size_t)h.n_ops * h.n_sites, c->stream, &c->op_allocs))) return rc;
+      G.acting_on = (const int32_t *)p;
+      if ((rc = upload<double>(&p, h.diag_mels, rows, c->stream, &c->op_allocs))) return rc;
+      G.diag_mels = (const double *)p;
+      if ((rc = upload<int32_t>(&p, h.n_conns, rows, c->stream, &c->op_allocs))) return rc;
+      G.n_conns = (const int32_t *)p;
+      if ((rc = upload<double>(&p, h.mels, rows * h.ncmax, c->stream, &c->op_allocs))) return rc;
+      G.mels = (const double *)p;
+      if ((rc = upload<int8_t>(&p, h.x_prime, rows * h.ncmax * h.n_sites, c->stream, &c->op_allocs))) return rc;
+      G.x_prime = (const int8_t *)p;
+    }
+    c->eloc_dtype = NK_F64;
+  }
+  // ... unless the caller asked for E_loc in the parameter dtype (the C-ABI v1 behaviour, kept by nk_ctx_create)
+  if (d->eloc_in_param_dtype) c->eloc_dtype = c->dtype;
+  c->eloc_esz = c->eloc_dtype == NK_F32 ? 4 : 8;
+  NK_CUDA_OK(cudaMalloc(&c->eloc, (size_t)B * c->chain_length * c->eloc_esz));
+  if (c->rule == NK_RULE_EXCHANGE) {
+    void *p = nullptr;
+    if ((rc = upload<int32_t>(&p, d->clusters_host, (size_t)2 * d->n_clusters, c->stream, nullptr))) return rc;
+    c->clusters = (int32_t *)p;
+    if ((rc = upload<double>(&p, d->cluster_probs_host, (size_t)d->n_clusters, c->stream, nullptr))) return rc;
+    c->cluster_probs = (double *)p;
+  }
+  {
+    nk_rbm_t shape{};
+    shape.W = c->W;
+    shape.N = N;
+    shape.M = M;
+    shape.dtype = c->dtype;
+    const int64_t wsb = nk_sweep_workspace_bytes(&shape, B);
+    if (wsb > 0) NK_CUDA_OK(cudaMalloc(&c->workspace, (size_t)wsb));
+  }
+  rc = random_state(c->stream, c->sigma, B, N, c->n_down, c->seed, c->chain_offset);
+  if (rc) return rc;
+  NK_CUDA_OK(cudaStreamSynchronize(c->stream));
+  *out = c;
+  return NK_OK;
 }
 
 int nk_ctx_create(nk_ctx **out, int32_t device, int32_t N, int32_t M, int32_t dtype, int64_t n_chains, int32_t chain_length,
@@ -492,52 +639,26 @@ int nk_ctx_create(nk_ctx **out, int32_t device, int32_t N, int32_t M, int32_t dt
   NK_CHECK_ARG(N > 0 && M > 0 && n_chains > 0 && chain_length > 0, "nk_ctx_create: bad sizes");
   NK_CHECK_ARG(dtype == NK_F32 || dtype == NK_F64, "nk_ctx_create: bad dtype");
   NK_CHECK_ARG(n_edges >= 0 && (n_edges == 0 || edges_host), "nk_ctx_create: bad edges");
-  NK_CUDA_OK(cudaSetDevice(device));
-  nk_ctx *c = new nk_ctx();
-  memset(c, 0, sizeof(*c));
-  c->device = device;
-  c->N = N;
-  c->M = M;
-  c->dtype = dtype;
-  c->B = n_chains;
-  c->chain_length = chain_length;
-  c->n_edges = n_edges;
-  c->esz = dtype == NK_F32 ? 4 : 8;
-  c->seed = seed;
-  c->t = 0;
-  c->chain_offset = chain_offset;
-  NK_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  NK_CUDA_OK(cudaMalloc(&c->W, (size_t)N * M * c->esz));
-  NK_CUDA_OK(cudaMalloc(&c->b, (size_t)M * c->esz));
-  NK_CUDA_OK(cudaMalloc(&c->a, (size_t)N * c->esz));
-  NK_CUDA_OK(cudaMalloc((void **)&c->sigma, (size_t)n_chains * N));
-  NK_CUDA_OK(cudaMalloc(&c->log_prob, (size_t)n_chains * c->esz));
-  NK_CUDA_OK(cudaMalloc((void **)&c->n_accepted, (size_t)n_chains * 8));
-  NK_CUDA_OK(cudaMalloc((void **)&c->edges, (size_t)(n_edges > 0 ? n_edges : 1) * 8));
-  NK_CUDA_OK(cudaMalloc(&c->eloc, (size_t)n_chains * chain_length * c->esz));
-  NK_CUDA_OK(cudaMalloc((void **)&c->partials, sizeof(double) * NK_STATS_NPARTIAL));
-  NK_CUDA_OK(cudaMalloc((void **)&c->nacc_sum, 8));
-  {
-    nk_rbm_t shape{};
-    shape.W = c->W;
-    shape.N = N;
-    shape.M = M;
-    shape.dtype = dtype;
-    const int64_t wsb = nk_sweep_workspace_bytes(&shape, n_chains);
-    if (wsb > 0) NK_CUDA_OK(cudaMalloc(&c->workspace, (size_t)wsb));
-  }
-  NK_CUDA_OK(cudaMallocHost((void **)&c->partials_host, sizeof(double) * NK_STATS_NPARTIAL));
-  NK_CUDA_OK(cudaMallocHost((void **)&c->nacc_host, 8));
-  if (n_edges > 0) NK_CUDA_OK(cudaMemcpyAsync(c->edges, edges_host, (size_t)n_edges * 8, cudaMemcpyHostToDevice, c->stream));
-  c->ising.edges = c->edges;
-  c->ising.n_edges = n_edges;
-  c->ising.h = h;
-  c->ising.J = J;
-  int rc = random_state(c->stream, c->sigma, n_chains, N, -1, seed, chain_offset);
-  if (rc) return rc;
-  NK_CUDA_OK(cudaStreamSynchronize(c->stream));
-  *out = c;
-  return NK_OK;
+  nk_ising_t op{};
+  op.edges = edges_host;
+  op.n_edges = n_edges;
+  op.h = h;
+  op.J = J;
+  nk_ctx_desc_t d{};
+  d.device = device;
+  d.N = N;
+  d.M = M;
+  d.dtype = dtype;
+  d.n_chains = n_chains;
+  d.chain_length = chain_length;
+  d.rule = NK_RULE_LOCAL;
+  d.machine_pow = 2.0;
+  d.n_down = -1;
+  d.ising_host = &op;
+  d.seed = seed;
+  d.chain_offset = chain_offset;
+  d.eloc_in_param_dtype = 1;
+  return nk_ctx_create2(out, &d);
 }
 
 void nk_ctx_destroy(nk_ctx *c) {
@@ -548,27 +669,33 @@ void nk_ctx_destroy(nk_ctx *c) {
   cudaFree(c->b);
   cudaFree(c->a);
   cudaFree(c->sigma);
+  cudaFree(c->samples);
   cudaFree(c->log_prob);
   cudaFree(c->n_accepted);
-  cudaFree(c->edges);
+  cudaFree(c->clusters);
+  cudaFree(c->cluster_probs);
   cudaFree(c->eloc);
   cudaFree(c->partials);
-  cudaFree(c->nacc_sum);
   cudaFree(c->workspace);
+  for (void *p : c->op_allocs) cudaFree(p);
   cudaFreeHost(c->partials_host);
-  cudaFreeHost(c->nacc_host);
-  cudaStreamDestroy(c->stream);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
 
-int nk_ctx_step_host(nk_ctx *c, const void *W_host, const void *b_host, const void *a_host, int32_t n_discard, void *eloc_host,
-                     double *stats_host) {
-  NK_CHECK_ARG(c && W_host && eloc_host && stats_host, "nk_ctx_step_host: NULL argument");
+void *nk_ctx_stream(nk_ctx *c) { return c ? (void *)c->stream : nullptr; }
+double *nk_ctx_partials_device(nk_ctx *c) { return c ? c->partials : nullptr; }
+
+int nk_ctx_step_begin(nk_ctx *c, const void *W_host, const void *b_host, const void *a_host, int32_t n_discard) {
+  NK_CHECK_ARG(c && W_host, "nk_ctx_step_begin: NULL argument");
+  NK_CHECK_ARG(n_discard >= 0, "nk_ctx_step_begin: n_discard < 0");
   NK_CUDA_OK(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
   NK_CUDA_OK(cudaMemcpyAsync(c->W, W_host, (size_t)c->N * c->M * c->esz, cudaMemcpyHostToDevice, st));
   if (b_host) NK_CUDA_OK(cudaMemcpyAsync(c->b, b_host, (size_t)c->M * c->esz, cudaMemcpyHostToDevice, st));
   if (a_host) NK_CUDA_OK(cudaMemcpyAsync(c->a, a_host, (size_t)c->N * c->esz, cudaMemcpyHostToDevice, st));
+  c->has_b = b_host != nullptr;
+  c->has_a = a_host != nullptr;
   nk_rbm_t rbm{};
   rbm.W = c->W;
   rbm.b = b_host ? c->b : nullptr;
@@ -588,38 +715,75 @@ int nk_ctx_step_host(nk_ctx *c, const void *W_host, const void *b_host, const vo
   ch.t = c->t;
   ch.chain_offset = c->chain_offset;
   nk_sweep_t a{};
-  a.rule = NK_RULE_LOCAL;
+  a.rule = c->rule;
   a.chain_length = c->chain_length;
   a.n_discard = n_discard;
-  a.sweep_size = c->N;
-  a.machine_pow = 2.0;
-  a.ising = &c->ising;
+  a.sweep_size = c->sweep_size;
+  a.machine_pow = c->machine_pow;
+  a.samples_out = c->samples;
+  a.clusters = c->clusters;
+  a.n_clusters = c->n_clusters;
+  a.cluster_probs = c->cluster_probs;
+  if (c->op_kind == 1)
+    a.ising = &c->ising;
+  else
+    a.localop = &c->localop;
   a.eloc_out = c->eloc;
-  a.eloc_dtype = c->dtype;
+  a.eloc_dtype = c->eloc_dtype;
   a.path = NK_PATH_AUTO;
+  a.stats_out = c->partials;  // the statistics' sums come out of the sweep kernel, shifted by the previous step's mean
+  a.stats_shift = c->shift;
   int rc = nk_sweep(st, &rbm, &ch, &a);
   if (rc) return rc;
   c->t = ch.t;
-  const int64_t L = c->chain_length;
-  NK_CUDA_OK(cudaMemcpyAsync(eloc_host, c->eloc, (size_t)c->B * L * c->esz, cudaMemcpyDeviceToHost, st));
-  // statistics: phase 0 -> mean, phase 1 -> shifted moments (single device: no all-reduce)
-  rc = stats_partial(st, c->eloc, c->dtype, c->B, L, 0, 0.0, c->partials);
-  if (rc) return rc;
-  NK_CUDA_OK(cudaMemcpyAsync(c->partials_host, c->partials, sizeof(double) * NK_STATS_NPARTIAL, cudaMemcpyDeviceToHost, st));
-  NK_CUDA_OK(cudaStreamSynchronize(st));
-  const double mean = c->partials_host[0] / ((double)c->B * (double)L);
-  rc = stats_partial(st, c->eloc, c->dtype, c->B, L, 1, mean, c->partials);
-  if (rc) return rc;
-  NK_CUDA_OK(cudaMemsetAsync(c->nacc_sum, 0, 8, st));
-  acc_sum_kernel<<<64, 256, 0, st>>>(c->n_accepted, c->B, (unsigned long long *)c->nacc_sum);
+  c->n_discard_last = n_discard;
+  ctx_tail_kernel<<<1, 1024, 0, st>>>(c->n_accepted, c->B, c->partials);
   NK_LAUNCH_OK();
-  NK_CUDA_OK(cudaMemcpyAsync(c->partials_host, c->partials, sizeof(double) * NK_STATS_NPARTIAL, cudaMemcpyDeviceToHost, st));
-  NK_CUDA_OK(cudaMemcpyAsync(c->nacc_host, c->nacc_sum, 8, cudaMemcpyDeviceToHost, st));
-  NK_CUDA_OK(cudaStreamSynchronize(st));
-  stats_finalize(c->partials_host, mean, c->B, L, stats_host);
-  const double n_steps = (double)c->B * (double)(n_discard + c->chain_length) * (double)c->N;
-  stats_host[5] = (double)(*c->nacc_host) / n_steps;
   return NK_OK;
+}
+
+int nk_ctx_step_end(nk_ctx *c, void *eloc_host, int8_t *samples_host, double *stats_host) {
+  NK_CHECK_ARG(c && eloc_host && stats_host, "nk_ctx_step_end: NULL argument");
+  NK_CHECK_ARG(samples_host == nullptr || c->return_samples, "nk_ctx_step_end: the context was created without return_samples");
+  NK_CUDA_OK(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const int64_t L = c->chain_length;
+  NK_CUDA_OK(cudaMemcpyAsync(eloc_host, c->eloc, (size_t)c->B * L * c->eloc_esz, cudaMemcpyDeviceToHost, st));
+  if (samples_host) NK_CUDA_OK(cudaMemcpyAsync(samples_host, c->samples, (size_t)c->B * L * c->N, cudaMemcpyDeviceToHost, st));
+  NK_CUDA_OK(cudaMemcpyAsync(c->partials_host, c->partials, sizeof(double) * NK_CTX_NPARTIAL, cudaMemcpyDeviceToHost, st));
+  NK_CUDA_OK(cudaStreamSynchronize(st));  // the one host synchronisation of a step
+  const double *p = c->partials_host;
+  const int64_t n_chains_total = (int64_t)llround(p[NK_STATS_NPARTIAL]);
+  NK_CHECK_ARG(n_chains_total > 0, "nk_ctx_step_end: the partial sums hold no chains (all-reduce gone wrong?)");
+  const double ts = (double)n_chains_total * (double)L;
+  const double dm = p[7] / ts, var = p[0] / ts - dm * dm;
+  int status = NK_OK;
+  if (!(dm * dm * (double)L <= 1.0e5 * var)) {
+    // the shift was too far from the mean for the one-pass formulas (first step, or a low-variance state)
+    if (n_chains_total == c->B) {  // single device: redo the sums in two passes around the mean just found
+      int rc = stats_partial(st, c->eloc, c->eloc_dtype, c->B, L, 1, c->shift + dm, c->partials);
+      if (rc) return rc;
+      NK_CUDA_OK(cudaMemcpyAsync(c->partials_host, c->partials, sizeof(double) * NK_STATS_NPARTIAL, cudaMemcpyDeviceToHost, st));
+      NK_CUDA_OK(cudaStreamSynchronize(st));
+      c->shift += dm;
+    } else {
+      status = NK_RESHIFT;  // multi-device: statistics below are valid to reduced precision; the next step's shift is the mean found
+    }
+  }
+  stats_finalize(c->partials_host, c->shift, n_chains_total, L, stats_host);
+  const double n_steps = (double)n_chains_total * (double)(c->n_discard_last + c->chain_length) * (double)c->sweep_size;
+  stats_host[5] = p[NK_STATS_NPARTIAL + 1] / n_steps;
+  c->shift = stats_host[0];
+  return status;
+}
+
+int nk_ctx_step_host(nk_ctx *c, const void *W_host, const void *b_host, const void *a_host, int32_t n_discard, void *eloc_host,
+                     double *stats_host) {
+  NK_CHECK_ARG(c && W_host && eloc_host && stats_host, "nk_ctx_step_host: NULL argument");
+  int rc = nk_ctx_step_begin(c, W_host, b_host, a_host, n_discard);
+  if (rc) return rc;
+  rc = nk_ctx_step_end(c, eloc_host, nullptr, stats_host);
+  return rc == NK_RESHIFT ? NK_OK : rc;
 }
 
 int nk_ctx_get_sigma_host(nk_ctx *c, int8_t *sigma_host) {

@@ -112,7 +112,8 @@ def sample_chain(
 
     stream: optional (w0[T,B] uint32, u[T,B]) explicit proposal stream, T = chain_length*sweep_size.
     Returns dict with samples[B,chain_length,N], log_prob_samples[B,chain_length], sigma, log_prob,
-    n_accepted[B] (int64), n_steps (= T*B, metropolis.py:459), t (= t0 + T).
+    n_accepted[B] (int64), n_steps (= T*B, metropolis.py:459), t (= t0 + T); with ``return_trace`` also
+    ``trace``: per step (selected site / cluster [B], accepted [B], margin [B] = log u - (logp' - logp + corr)).
     """
     sigma = np.array(sigma, dtype=np.int8, copy=True)
     B, N = sigma.shape
@@ -156,7 +157,9 @@ def sample_chain(
             logp = np.where(acc, logp_p, logp)
             n_acc += acc
             if return_trace:
-                trace.append((sel.copy(), acc.copy()))
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    margin = np.log(u[t].astype(np.float64)) - arg.astype(np.float64)  # accept <=> margin < 0
+                trace.append((sel.copy(), acc.copy(), margin))
             t += 1
         samples[:, s, :] = sigma
         lps[:, s] = logp

@@ -1,0 +1,168 @@
+"""BASELINE.json configurations at their stated size against the CPU oracle (not only against another CUDA path).
+
+The headline launches run all their chains; the oracle re-runs a subsample of them - chains spread over every round of the
+warp-major chain dealing (first / last chains, the partial last round) - with the same Philox stream (keyed by the global
+chain index), and re-evaluates the local energy of randomly chosen (chain, sweep) pairs of the kernel's own samples.
+fp64: chains bit for bit, E_loc to north_star's 1e-12; fp32: E_loc to 1e-5, chains identical except where the oracle's
+own accept margin |log u - machine_pow * delta| in the first differing sweep is inside fp32's resolution (a tie).
+cfg-5 (N=400, M=3200: several warps per chain, table read through L2) is run at its real instantiation on few chains.
+"""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import estimators as oest
+from oracle import graph as ograph
+from oracle import operators as oops
+from oracle import rbm as orbm
+from oracle import rng as orng
+from oracle import sampler as osampler
+
+pytestmark = pytest.mark.gpu
+
+F64_TOL, F32_TOL = 1e-12, 1e-5   # north_star: logpsi / E_loc relative tolerances
+TIE_BAND = 1e-4                  # |margin| below which an fp32 accept decision may legitimately differ from the fp64 oracle's
+
+
+def _nk():
+    import netket_b200 as nk
+
+    return nk
+
+
+def _var(N, alpha, dtype, std=0.01, seed=1234):
+    W, b, a = orbm.init_params(N, alpha, seed=seed, std=std, dtype=dtype)
+    var = {"params": {"Dense": {"kernel": torch.from_numpy(W).cuda(), "bias": torch.from_numpy(b).cuda()},
+                      "visible_bias": torch.from_numpy(a).cuda()}}
+    return (W.astype(np.float64), b.astype(np.float64), a.astype(np.float64)), var
+
+
+def assert_rel(x, ref, tol, what=""):
+    """Element-wise relative error; values below 1 % of the largest magnitude are held to an absolute floor of tol * 1 % * max."""
+    x, ref = np.asarray(x, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    np.testing.assert_allclose(x, ref, rtol=tol, atol=tol * 0.01 * np.abs(ref).max(), err_msg=what)
+
+
+def _spread(B, n, slots, rs):
+    """n chain indices: the first and last chains, chains of the last (partial) round of `slots` resident chains, random others."""
+    last_round = np.arange((B // slots) * slots, B) if B % slots else np.arange(B - slots, B)
+    pick = np.concatenate([[0, 1, B - 1, B - 2], rs.choice(last_round, size=min(8, len(last_round)), replace=False),
+                           rs.choice(B, size=n, replace=False)])
+    return np.unique(pick)[:n + 12]
+
+
+def _oracle_chains(rule, sig0, ids, W, b, a, seed, t0, n_sweeps, sweep_size, dtype, clusters=None):
+    words, u = orng.proposal_stream(seed, t0, n_sweeps * sweep_size, ids.astype(np.uint64), dtype)
+    return osampler.sample_chain(rule, sig0[ids], W, b, a, chain_length=n_sweeps, sweep_size=sweep_size,
+                                 stream=(words[..., 0], u.astype(np.float64)), clusters=clusters, return_trace=True)
+
+
+def _check_fp32_chains(samples, ref, n_discard, sweep_size):
+    """fp32 chains vs the fp64 oracle on the same stream: identical, or first different in a sweep that holds a tie."""
+    got = samples
+    want = ref["samples"][:, n_discard:]
+    same = np.all(got == want, axis=(1, 2))
+    margins = np.stack([m for _, _, m in ref["trace"]], axis=0)  # [T, B]
+    for c in np.nonzero(~same)[0]:
+        first = int(np.nonzero(np.any(got[c] != want[c], axis=1))[0][0]) + n_discard  # first differing recorded sweep
+        # the departure may also have happened in an unrecorded (burn-in) sweep before it
+        lo = 0 if first == n_discard else first * sweep_size
+        m = np.abs(margins[lo:(first + 1) * sweep_size, c])
+        assert np.nanmin(m) < TIE_BAND, f"chain {c} departs from the oracle in sweep {first} without a near-tie (min |margin| {np.nanmin(m):.2e})"
+    return same.mean()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_cfg3_full_size_subsample_vs_oracle(cuda, dtype):
+    """cfg-3 exactly as bench.py runs it: 2^16 chains, 5 burn-in + 16 recorded sweeps, fused TFIM local energy."""
+    nk = _nk()
+    B, CL, ND = 1 << 16, 16, 5
+    g = nk.graph.Hypercube(10, 2)
+    hi = nk.hilbert.Spin(0.5, 100)
+    op = nk.operator.Ising(hi, g, h=3.0)
+    e, _ = ograph.hypercube_edges(10, 2)
+    (W, b, a), var = _var(100, 4, dtype)
+    model = nk.models.RBM(alpha=4, param_dtype=dtype)
+    sa = nk.sampler.MetropolisLocal(hi, n_chains=B)
+    st0 = sa.init_state(model, var, seed=15324)
+    seed, t0 = st0.rng
+    samples, _, eloc, st = sa._launch(model, var, st0, CL, n_discard=ND, operator=op)
+    rs = np.random.default_rng(1)
+    # ---- local energies of 768 (chain, sweep) pairs of the kernel's own samples
+    cs, ts = rs.integers(0, B, size=768), rs.integers(0, CL, size=768)
+    conf = samples[torch.from_numpy(cs).cuda(), torch.from_numpy(ts).cuda()].cpu().numpy()
+    ref_e = oest.local_value_kernel(conf, lambda x: oops.ising_conn_padded(x, e, 3.0, 1.0), W, b, a)
+    got_e = eloc[torch.from_numpy(cs).cuda(), torch.from_numpy(ts).cuda()].cpu().numpy()
+    assert_rel(got_e, ref_e, F64_TOL if dtype == np.float64 else F32_TOL, "fused E_loc")
+    # ---- whole chains
+    ids = _spread(B, 52, 148 * 28 if dtype == np.float32 else 148 * 12, rs)
+    ref = _oracle_chains("local", st0.σ.cpu().numpy(), ids, W, b, a, seed, t0, ND + CL, 100, dtype)
+    got = samples[torch.from_numpy(ids).cuda()].cpu().numpy()
+    if dtype == np.float64:
+        assert np.array_equal(got, ref["samples"][:, ND:])
+        assert np.array_equal(st.n_accepted_proc[torch.from_numpy(ids).cuda()].cpu().numpy(), ref["n_accepted"])
+        np.testing.assert_allclose(st.log_prob[torch.from_numpy(ids).cuda()].cpu().numpy(), ref["log_prob"], rtol=1e-10)
+    else:
+        frac = _check_fp32_chains(got, ref, ND, 100)
+        assert frac >= 0.8, frac
+
+
+def test_cfg4_full_size_subsample_vs_oracle(cuda):
+    """cfg-4: J1-J2 10x10, RBM alpha=4 fp64, MetropolisExchange, 2^14 chains x 16 = 2^18 samples, fused LocalOperator E_loc."""
+    nk = _nk()
+    B, CL, ND = 1 << 14, 16, 2
+    g = nk.graph.Hypercube(10, 2, max_neighbor_order=2)
+    hi = nk.hilbert.Spin(0.5, 100, total_sz=0)
+    op = nk.operator.Heisenberg(hi, g, J=[1.0, 0.5], sign_rule=[False, False])
+    (W, b, a), var = _var(100, 4, np.float64)
+    model = nk.models.RBM(alpha=4)
+    sa = nk.sampler.MetropolisExchange(hi, graph=g, d_max=1, n_chains=B)
+    st0 = sa.init_state(model, var, seed=15324)
+    seed, t0 = st0.rng
+    samples, _, eloc, st = sa._launch(model, var, st0, CL, n_discard=ND, operator=op)
+    rs = np.random.default_rng(2)
+    e, col = ograph.hypercube_edges(10, 2, True, 2)
+    tables = oops.heisenberg_tables(e, col, [1.0, 0.5], [False, False])
+    cs, ts = rs.integers(0, B, size=192), rs.integers(0, CL, size=192)
+    conf = samples[torch.from_numpy(cs).cuda(), torch.from_numpy(ts).cuda()].cpu().numpy()
+    ref_e = oest.local_value_kernel(conf, lambda x: oops.local_operator_conn_padded(x, tables), W, b, a)
+    assert_rel(eloc[torch.from_numpy(cs).cuda(), torch.from_numpy(ts).cuda()].cpu().numpy(), ref_e, F64_TOL, "fused J1-J2 E_loc")
+    ids = _spread(B, 36, 148 * 12, rs)
+    e1, _ = ograph.hypercube_edges(10, 2)
+    clusters = ograph.compute_clusters(100, e1, 1)
+    assert np.array_equal(clusters, sa.rule.clusters)
+    ref = _oracle_chains("exchange", st0.σ.cpu().numpy(), ids, W, b, a, seed, t0, ND + CL, 100, np.float64, clusters=clusters)
+    assert np.array_equal(samples[torch.from_numpy(ids).cuda()].cpu().numpy(), ref["samples"][:, ND:])
+    assert np.array_equal(st.n_accepted_proc[torch.from_numpy(ids).cuda()].cpu().numpy(), ref["n_accepted"])
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_cfg5_instantiation_vs_oracle(cuda, dtype):
+    """cfg-5's kernel (TFIM 20x20, RBM alpha=8: N=400, M=3200 -> 10 warps per chain, rows through L2) on 40 chains x 2 sweeps:
+    chain (fp64: bit for bit) and fused E_loc against the oracle; fp32 on NK_PATH_AUTO, i.e. what a user gets."""
+    nk = _nk()
+    B, CL = 40, 2
+    g = nk.graph.Hypercube(20, 2)
+    hi = nk.hilbert.Spin(0.5, 400)
+    op = nk.operator.Ising(hi, g, h=3.0)
+    e, _ = ograph.hypercube_edges(20, 2)
+    (W, b, a), var = _var(400, 8, dtype)
+    model = nk.models.RBM(alpha=8, param_dtype=dtype)
+    sa = nk.sampler.MetropolisLocal(hi, n_chains=B)
+    st0 = sa.init_state(model, var, seed=15324)
+    seed, t0 = st0.rng
+    samples, logp, eloc, st = sa._launch(model, var, st0, CL, n_discard=0, operator=op, return_log_probabilities=True)
+    ref = _oracle_chains("local", st0.σ.cpu().numpy(), np.arange(B), W, b, a, seed, t0, CL, 400, dtype)
+    got = samples.cpu().numpy()
+    ref_e = oest.local_estimators(got, lambda x: oops.ising_conn_padded(x, e, 3.0, 1.0), W, b, a)
+    if dtype == np.float64:
+        assert np.array_equal(got, ref["samples"])
+        np.testing.assert_allclose(logp.cpu().numpy(), ref["log_prob_samples"], rtol=1e-10)
+        assert_rel(eloc.cpu().numpy(), ref_e, F64_TOL, "cfg-5 E_loc fp64")
+    else:
+        assert _check_fp32_chains(got, ref, 0, 400) >= 0.8
+        assert_rel(eloc.cpu().numpy(), ref_e, F32_TOL, "cfg-5 E_loc fp32")
+    # the stand-alone estimator takes the same kernel family (theta GEMM for N > 128 / M > 512, then the E_loc code)
+    vs = nk.vqs.MCState(sa, model, variables=var, n_samples=B, seed=1)
+    assert_rel(vs._eloc_on_samples(op, samples).cpu().numpy(), ref_e, F64_TOL if dtype == np.float64 else F32_TOL, "stand-alone")

@@ -338,10 +338,11 @@ def test_fused_eloc_equals_standalone_and_oracle(cuda, dtype):
     e, _ = ograph.hypercube_edges(4, 2)
     ref = oest.local_estimators(samples.cpu().numpy(), lambda x: oops.ising_conn_padded(x, e, 3.0, 1.0), W.astype(np.float64),
                                 b.astype(np.float64), a.astype(np.float64))
-    tol = RTOL[dtype] if dtype == np.float64 else 2e-5
-    np.testing.assert_allclose(eloc_alone.cpu().numpy(), ref, rtol=tol, atol=tol * np.abs(ref).max())
-    np.testing.assert_allclose(eloc_fused.cpu().numpy(), ref, rtol=tol * (1 if dtype == np.float32 else 1e3),
-                               atol=tol * (1 if dtype == np.float32 else 1e3) * np.abs(ref).max())
+    from tolerances import F32_TOL, F64_TOL, assert_rel
+
+    tol = F64_TOL if dtype == np.float64 else F32_TOL
+    assert_rel(eloc_alone.cpu().numpy(), ref, tol, "stand-alone E_loc (theta form)")
+    assert_rel(eloc_fused.cpu().numpy(), ref, tol, "fused E_loc")
     st = vs.expect(op)
     ost = oracle.stats.statistics(eloc_fused.cpu().numpy())
     for k in ("mean", "variance", "error_of_mean", "tau_corr", "R_hat"):

@@ -17,6 +17,7 @@ from oracle import operators as oops
 from oracle import rbm as orbm
 from oracle import rng as orng
 from oracle import sampler as osampler
+from tolerances import F32_TOL, F32_TOL_LARGE_W, F64_TOL, assert_rel
 
 pytestmark = pytest.mark.gpu
 
@@ -154,8 +155,8 @@ def test_prod_fused_eloc_ising(cuda, dtype, L, n_dim, alpha, std, h, CL):
     W64, b64, a64 = _f64(W, b, a)
     ref = oest.local_estimators(samples.cpu().numpy(), lambda x: oops.ising_conn_padded(x, e, h, 1.0), W64, b64, a64)
     assert eloc.dtype == torch.float64
-    tol = 1e-11 if dtype == np.float64 else 1e-5
-    np.testing.assert_allclose(eloc.cpu().numpy(), ref, rtol=tol, atol=tol * np.abs(ref).max())
+    tol = F64_TOL if dtype == np.float64 else F32_TOL
+    assert_rel(eloc.cpu().numpy(), ref, tol)
 
 
 def _heis(nk, L, n_dim, total_sz, J, sign_rule, order=1):
@@ -187,8 +188,8 @@ def test_prod_fused_eloc_heisenberg(cuda, dtype, rule, L, n_dim, total_sz, J, si
     samples, _, eloc, _ = sa._launch(model, var, st, 4, n_discard=1, operator=op, path=PROD)
     W64, b64, a64 = _f64(W, b, a)
     ref = oest.local_estimators(samples.cpu().numpy(), lambda x: oops.local_operator_conn_padded(x, tables), W64, b64, a64)
-    tol = 1e-11 if dtype == np.float64 else 2e-5
-    np.testing.assert_allclose(eloc.cpu().numpy(), ref, rtol=tol, atol=tol * np.abs(ref).max())
+    tol = F64_TOL if dtype == np.float64 else F32_TOL
+    assert_rel(eloc.cpu().numpy(), ref, tol)
     if total_sz is not None:
         assert np.all(samples.cpu().numpy().astype(int).sum(axis=-1) == round(2 * total_sz))
     # the generic kernel on the same start state and stream gives the same chain in fp64, hence the same E_loc
@@ -220,8 +221,8 @@ def test_prod_fused_eloc_general_local_operator(cuda, dtype):
     samples, _, eloc, _ = sa._launch(model, var, st, 3, operator=op, path=PROD)
     W64, b64, a64 = _f64(W, b, a)
     ref = oest.local_estimators(samples.cpu().numpy(), lambda x: oops.local_operator_conn_padded(x, tables), W64, b64, a64)
-    tol = 1e-11 if dtype == np.float64 else 2e-5
-    np.testing.assert_allclose(eloc.cpu().numpy(), ref, rtol=tol, atol=tol * np.abs(ref).max())
+    tol = F64_TOL if dtype == np.float64 else F32_TOL
+    assert_rel(eloc.cpu().numpy(), ref, tol)
 
 
 # ----------------------------------------------------------------------------------------- hand-over, statistics
@@ -296,8 +297,8 @@ def test_prod_standalone_eloc(cuda, dtype, kind, L, n_dim, alpha, std):
     out = vs._eloc_on_samples(op, torch.from_numpy(sig).cuda(), path=PROD)
     assert tuple(out.shape) == (3, 67) and out.dtype == torch.float64
     ref = oest.local_value_kernel(sig.reshape(-1, N), conn, *_f64(W, b, a)).reshape(3, 67)
-    tol = 1e-12 if dtype == np.float64 else 1e-5
-    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=tol, atol=tol * np.abs(ref).max())
+    tol = F64_TOL if dtype == np.float64 else F32_TOL
+    assert_rel(out.cpu().numpy(), ref, tol)
     gen = vs._eloc_on_samples(op, torch.from_numpy(sig).cuda(), path=1)
     np.testing.assert_allclose(out.cpu().numpy(), gen.cpu().numpy(), rtol=2 * tol, atol=2 * tol * np.abs(ref).max())
     auto = vs._eloc_on_samples(op, torch.from_numpy(sig).cuda(), path=0)
@@ -362,8 +363,8 @@ def test_prod_large_fused_eloc(cuda, dtype, rule, L, n_dim, alpha, std, total_sz
     st = sa.init_state(model, var, seed=11)
     samples, _, eloc, st2 = sa._launch(model, var, st, 2, n_discard=1, operator=op, path=PROD)
     ref = oest.local_estimators(samples.cpu().numpy(), conn, *_f64(W, b, a))
-    tol = 1e-11 if dtype == np.float64 else 2e-5
-    np.testing.assert_allclose(eloc.cpu().numpy(), ref, rtol=tol, atol=tol * np.abs(ref).max())
+    tol = F64_TOL if dtype == np.float64 else F32_TOL
+    assert_rel(eloc.cpu().numpy(), ref, tol)
     # fp32: the chain itself follows the oracle's up to accept-boundary ties
     if dtype == np.float32:
         seed, t0 = st.rng
@@ -375,7 +376,7 @@ def test_prod_large_fused_eloc(cuda, dtype, rule, L, n_dim, alpha, std, total_sz
     # stand-alone estimator on the same samples
     vs = nk.vqs.MCState(sa, model, variables=var, n_samples=B, seed=1)
     alone = vs._eloc_on_samples(op, samples, path=PROD)
-    np.testing.assert_allclose(alone.cpu().numpy(), ref, rtol=tol, atol=tol * np.abs(ref).max())
+    assert_rel(alone.cpu().numpy(), ref, tol)
 
 
 # ----------------------------------------------------------------------------------------- edge shapes
@@ -407,7 +408,7 @@ def test_prod_edge_shapes_fp64(cuda, N, M, B, CL, sweep_size):
     assert np.array_equal(st2.n_accepted_proc.cpu().numpy(), ref["n_accepted"])
     e = np.asarray(g.edges(), dtype=np.int64).reshape(-1, 2)
     eref = oest.local_estimators(ref["samples"], lambda x: oops.ising_conn_padded(x, e, 0.7, 1.0), W, b, a)
-    np.testing.assert_allclose(eloc.cpu().numpy(), eref, rtol=1e-11, atol=1e-11 * max(1.0, np.abs(eref).max()))
+    assert_rel(eloc.cpu().numpy(), eref, F64_TOL)
 
 
 def test_prod_burn_in_only_and_empty_batch(cuda):
@@ -492,8 +493,8 @@ def test_prod_without_biases(cuda, dtype, hb, vb):
     b64 = None if b is None else b.astype(np.float64)
     a64 = None if a is None else a.astype(np.float64)
     ref = oest.local_estimators(samples.cpu().numpy(), lambda x: oops.ising_conn_padded(x, e, 1.1, 1.0), W64, b64, a64)
-    tol = 1e-11 if dtype == np.float64 else 1e-5
-    np.testing.assert_allclose(eloc.cpu().numpy(), ref, rtol=tol, atol=tol * np.abs(ref).max())
+    tol = F64_TOL if dtype == np.float64 else F32_TOL
+    assert_rel(eloc.cpu().numpy(), ref, tol)
     if dtype == np.float64:
         seed, t0 = st.rng
         r = osampler.sample_chain("local", st.σ.cpu().numpy(), W64, b64, a64, chain_length=3, seed=seed, t0=t0)
@@ -561,14 +562,14 @@ def test_prod_local_operator_edge_cases(cuda, dtype):
     st = sa.init_state(model, var, seed=6)
     sx = np.array([[0.0, 1.0], [1.0, 0.0]])
     sz = np.array([[1.0, 0.0], [0.0, -1.0]])
-    tol = 1e-11 if dtype == np.float64 else 2e-5
+    tol = F64_TOL if dtype == np.float64 else F32_TOL
     W64, b64, a64 = _f64(W, b, a)
     # transverse field as LocalOperator == Ising(h, J=0)
     op_x = nk.operator.LocalOperator(hi, [-1.3 * sx] * N, [[i] for i in range(N)])
     samples, _, e_x, _ = sa._launch(model, var, st, 2, operator=op_x, path=PROD)
     e, _ = ograph.hypercube_edges(N, 1)
     ref = oest.local_estimators(samples.cpu().numpy(), lambda x: oops.ising_conn_padded(x, e, 1.3, 0.0), W64, b64, a64)
-    np.testing.assert_allclose(e_x.cpu().numpy(), ref, rtol=tol, atol=tol * np.abs(ref).max())
+    assert_rel(e_x.cpu().numpy(), ref, tol)
     # constant + diagonal terms only, with an off-diagonal entry below the cutoff and a duplicated term
     tiny = np.array([[0.0, 1e-12], [1e-12, 0.0]])
     ops = [0.5 * sz, tiny, 0.5 * sz, np.kron(sz, sz)]
@@ -577,7 +578,7 @@ def test_prod_local_operator_edge_cases(cuda, dtype):
     tables = oops.pack_internals(oops.canonical_operators_dict(ops, aon), 0.7)
     samples, _, e_d, _ = sa._launch(model, var, st, 2, operator=op_d, path=PROD)
     ref = oest.local_estimators(samples.cpu().numpy(), lambda x: oops.local_operator_conn_padded(x, tables), W64, b64, a64)
-    np.testing.assert_allclose(e_d.cpu().numpy(), ref, rtol=tol, atol=tol * np.abs(ref).max())
+    assert_rel(e_d.cpu().numpy(), ref, tol)
     s = samples.cpu().numpy().astype(np.float64)
     np.testing.assert_allclose(e_d.cpu().numpy(), 0.7 + s[..., 0] + s[..., 2] * s[..., 3], rtol=tol, atol=tol)
 
@@ -605,7 +606,7 @@ def test_auto_path_boundaries_fp32(cuda, N, M):
     W64, b64, a64 = _f64(W, b, a)
     e = np.asarray(g.edges(), dtype=np.int64).reshape(-1, 2)
     ref = oest.local_estimators(samples.cpu().numpy(), lambda x: oops.ising_conn_padded(x, e, 1.0, 1.0), W64, b64, a64)
-    np.testing.assert_allclose(eloc.cpu().numpy(), ref, rtol=2e-5, atol=2e-5 * np.abs(ref).max())
+    assert_rel(eloc.cpu().numpy(), ref, F32_TOL)
     seed, t0 = st.rng
     words, u32 = orng.proposal_stream(seed, t0, CL * N, np.arange(B), np.float32)
     r = osampler.sample_chain("local", st.σ.cpu().numpy(), W64, b64, a64, chain_length=CL, stream=(words[..., 0], u32.astype(np.float64)))
@@ -639,8 +640,8 @@ def test_prod_wide_range_weights(cuda, dtype, std, expect_split, expect_wide_e):
     assert flags[1] >= 1 and flags[6] == expect_split and flags[7] == expect_wide_e, flags[:8]
     W64, b64, a64 = _f64(W, b, a)
     ref = oest.local_estimators(samples.cpu().numpy(), lambda x: oops.ising_conn_padded(x, e, 3.0, 1.0), W64, b64, a64)
-    tol = 1e-10 if dtype == np.float64 else 3e-5
-    np.testing.assert_allclose(eloc.cpu().numpy(), ref, rtol=tol, atol=tol * np.abs(ref).max())
+    tol = F64_TOL if dtype == np.float64 else F32_TOL_LARGE_W
+    assert_rel(eloc.cpu().numpy(), ref, tol)
     seed, t0 = st.rng
     if dtype == np.float64:
         r = osampler.sample_chain("local", st.σ.cpu().numpy(), W64, b64, a64, chain_length=CL + 1, seed=seed, t0=t0)
@@ -666,7 +667,7 @@ def test_fp32_auto_chain_large_weights(cuda, std, fast_gives_up, prod_gives_up):
     assert (int(flags[0] != 0), int(flags[5] != 0)) == (fast_gives_up, prod_gives_up), flags[:8]
     W64, b64, a64 = _f64(W, b, a)
     ref = oest.local_estimators(samples.cpu().numpy(), lambda x: oops.ising_conn_padded(x, e, 3.0, 1.0), W64, b64, a64)
-    np.testing.assert_allclose(eloc.cpu().numpy(), ref, rtol=3e-5, atol=3e-5 * np.abs(ref).max())
+    assert_rel(eloc.cpu().numpy(), ref, F32_TOL_LARGE_W)
     seed, t0 = st.rng
     words, u32 = orng.proposal_stream(seed, t0, (CL + 1) * 100, np.arange(B), np.float32)
     r = osampler.sample_chain("local", st.σ.cpu().numpy(), W64, b64, a64, chain_length=CL + 1, stream=(words[..., 0], u32.astype(np.float64)))
