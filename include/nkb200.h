@@ -199,6 +199,15 @@ int nk_stats_partial(void *stream, const void *data, int32_t dtype, int64_t n_ch
  * out_host = {mean, error_of_mean, variance, tau_corr, R_hat} */
 int nk_stats_finalize(const double *sums_host, double shift, int64_t n_chains_total, int64_t L, double *out_host);
 
+/* Integrated autocorrelation time of every chain with Sokal's automatic window: the tau_corr / tau_corr_max of the opt-in FFT
+ * variant of `statistics` (netket/stats/mc_stats.py:303-331, netket/stats/_autocorr.py:40-86; the autocorrelation function the
+ * reference obtains by a zero-padded FFT is summed directly, lag by lag, up to the window).  data [n_chains, L] (dtype), c: the
+ * window constant (5).  out (3 doubles, device, zeroed by the call): out[0] = sum of the chains' tau, out[1] = their maximum in an
+ * order-preserving integer encoding (combine across GPUs with an integer / bitwise-ordered MAX, decode with
+ * nk_stats_tau_max_decode on the host), out[2] = number of chains whose tau is NaN (zero variance). */
+int nk_stats_tau(void *stream, const void *data, int32_t dtype, int64_t n_chains, int64_t L, double c, double *out);
+double nk_stats_tau_max_decode(double encoded);
+
 /* Streaming statistics: OnlineStats (netket/_src/stats/online_stats/accumulator.py:31-447), the accumulator behind
  * thermalise_mcmc / check_mc_convergence / expect_to_precision (netket/_src/vqs/check_mc_convergence.py,
  * expect_to_precision.py).  The state is the reference's pytree, field for field, as device arrays of doubles:

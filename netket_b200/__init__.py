@@ -14,5 +14,6 @@ Scope: SURVEY.md §8 / DESIGN.md.  There is no CPU path: every numerical entry p
 
 from . import convergence, driver, graph, hilbert, models, operator, optimizer, sampler, serialization, stats, vqs  # noqa: F401
 from ._lib import NkError, LIB_PATH  # noqa: F401
+from .config import config  # noqa: F401
 
 __version__ = "0.1.0"

@@ -103,6 +103,8 @@ SYMBOLS = {
     "nk_forces_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_int64, C.c_void_p, C.c_int32]),
     "nk_stats_partial": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_double, C.c_void_p]),
     "nk_stats_finalize": (C.c_int, [C.POINTER(C.c_double), C.c_double, C.c_int64, C.c_int64, C.POINTER(C.c_double)]),
+    "nk_stats_tau": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_double, C.c_void_p]),
+    "nk_stats_tau_max_decode": (C.c_double, [C.c_double]),
     "nk_rbm_tanh_theta": (C.c_int, [C.c_void_p, C.POINTER(nk_rbm_t), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "nk_rbm_jvp": (C.c_int, [C.c_void_p, C.POINTER(nk_rbm_t), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                              C.c_void_p]),

@@ -1,4 +1,5 @@
 // extern "C" entry points of libnkb200 (see include/nkb200.h): argument validation, path selection, launches.
+#include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -49,6 +50,7 @@ int localop_conn(cudaStream_t stream, const nk_localop_t &op, const int8_t *x, i
 int stats_partial(cudaStream_t stream, const void *data, int32_t dtype, int64_t n_chains, int64_t L, int32_t phase, double shift,
                   double *out, const int *run_if = nullptr);
 int stats_finalize(const double *p, double mean, int64_t n_chains, int64_t L, double *out);
+int stats_tau(cudaStream_t stream, const void *data, int32_t dtype, int64_t n_chains, int64_t L, double c, double *out);
 int rbm_tanh_inplace(cudaStream_t stream, void *x, int32_t dtype, int64_t n);
 int rbm_jvp_dot(cudaStream_t stream, const nk_rbm_t &v, const int8_t *sigma, int64_t Ns, const void *t, const void *g, double *y,
                 double *y_sum);
@@ -388,6 +390,23 @@ int nk_stats_partial(void *stream, const void *data, int32_t dtype, int64_t n_ch
   NK_CHECK_ARG(phase == 0 || phase == 1, "nk_stats_partial: phase must be 0 or 1");
   NK_CHECK_ARG(n_chains * L == 0 || data, "nk_stats_partial: NULL data");
   return stats_partial((cudaStream_t)stream, data, dtype, n_chains, L, phase, shift, partials_out);
+}
+
+int nk_stats_tau(void *stream, const void *data, int32_t dtype, int64_t n_chains, int64_t L, double c, double *out) {
+  NK_CHECK_ARG(dtype == NK_F32 || dtype == NK_F64, "nk_stats_tau: bad dtype");
+  NK_CHECK_ARG(n_chains >= 0 && L >= 0 && out && c > 0.0, "nk_stats_tau: bad arguments");
+  NK_CHECK_ARG(n_chains * L == 0 || data, "nk_stats_tau: NULL data");
+  return stats_tau((cudaStream_t)stream, data, dtype, n_chains, L, c, out);
+}
+
+double nk_stats_tau_max_decode(double encoded) {
+  unsigned long long e;
+  memcpy(&e, &encoded, 8);
+  if (e == 0ull) return NAN;  // no chain contributed
+  const unsigned long long b = (e >> 63) ? (e & 0x7fffffffffffffffull) : ~e;
+  double v;
+  memcpy(&v, &b, 8);
+  return v;
 }
 
 int nk_rbm_tanh_theta(void *stream, const nk_rbm_t *rbm, const int8_t *samples, int64_t Ns, void *out, void *workspace) {

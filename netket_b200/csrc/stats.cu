@@ -106,6 +106,99 @@ int stats_partial(cudaStream_t stream, const void *data, int32_t dtype, int64_t 
   return NK_OK;
 }
 
+// ---- integrated autocorrelation time per chain, Sokal's automatic window (the opt-in FFT variant of `statistics`:
+// netket/stats/mc_stats.py:303-331 with netket/stats/_autocorr.py:40-86).  The reference evaluates the autocorrelation function
+// acf[k] = sum_t d_t d_{t+k}, d = x - mean(x), with a zero-padded FFT; the same sums are taken directly here, lag by lag, and
+// the scan stops at the window: tau(M) = 2 sum_{k<=M} acf[k]/acf[0] - 1 at the first M with M >= c tau(M) (`auto_window`:
+// argmin(M < c tau) - 0 if every M qualifies, the last M if none does).  One warp per chain; out[0] += sum of the chains'
+// tau, out[1] = max tau (as ordered bits, see tau_decode), out[2] += number of chains whose tau is NaN.
+__device__ __forceinline__ unsigned long long tau_encode(double v) {  // order-preserving map double -> u64
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) stats_tau_kernel(const T *__restrict__ data, int64_t n_chains, int64_t L, double c, double *__restrict__ out) {
+  extern __shared__ double tsm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  double *d = tsm + (size_t)warp * L;
+  for (int64_t ch = (int64_t)blockIdx.x * warps + warp; ch < n_chains; ch += (int64_t)gridDim.x * warps) {
+    const T *row = data + ch * L;
+    double s = 0.0;
+    for (int64_t i = lane; i < L; i += 32) s += (double)row[i];
+    const double mean = warp_sum(s) / (double)L;
+    for (int64_t i = lane; i < L; i += 32) d[i] = (double)row[i] - mean;
+    __syncwarp();
+    double acf0 = 0.0, cum = 0.0, tau = 0.0, tau0 = 0.0;
+    bool any_true = false, found = false;
+    int64_t k = 0;
+    for (; k < L; ++k) {
+      double a = 0.0;
+      for (int64_t t = lane; t + k < L; t += 32) a += d[t] * d[t + k];
+      a = warp_sum(a);
+      if (k == 0) acf0 = a;
+      cum += a / acf0;
+      tau = 2.0 * cum - 1.0;
+      if (k == 0) tau0 = tau;
+      if ((double)k < c * tau) {
+        any_true = true;
+      } else {  // first False entry of m: the window (if any entry is True at all)
+        found = true;
+        break;
+      }
+    }
+    double res;
+    if (found) {
+      if (!any_true) {
+        // no M with M < c tau: the reference takes the last M; finish the cumulative sum
+        for (++k; k < L; ++k) {
+          double a = 0.0;
+          for (int64_t t = lane; t + k < L; t += 32) a += d[t] * d[t + k];
+          cum += warp_sum(a) / acf0;
+        }
+        res = 2.0 * cum - 1.0;
+      } else {
+        res = tau;
+      }
+    } else {
+      res = tau0;  // every M qualifies: argmin of an all-True mask is 0
+    }
+    if (lane == 0) {
+      if (res != res) {
+        atomicAdd(out + 2, 1.0);
+      } else {
+        atomicAdd(out + 0, res);
+        atomicMax(reinterpret_cast<unsigned long long *>(out + 1), tau_encode(res));
+      }
+    }
+    __syncwarp();
+  }
+}
+
+int stats_tau(cudaStream_t stream, const void *data, int32_t dtype, int64_t n_chains, int64_t L, double c, double *out) {
+  NK_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(double) * 3, stream));  // out[1] = 0 bits: below the encoding of every double
+  if (n_chains == 0 || L == 0) return NK_OK;
+  int warps = 8;
+  while (warps > 1 && (size_t)warps * L * 8 > 200 * 1024) warps >>= 1;
+  const size_t smem = (size_t)warps * L * 8;
+  if (smem > 200 * 1024) {
+    set_error("nk_stats_tau: chains of %lld samples do not fit shared memory (max 25600)", (long long)L);
+    return NK_EUNSUPPORTED;
+  }
+  const int64_t need = (n_chains + warps - 1) / warps;
+  const int64_t cap = (int64_t)num_sms() * 4;
+  const int grid = (int)(need < cap ? need : cap);
+  if (dtype == NK_F32) {
+    NK_CUDA_OK(cudaFuncSetAttribute(stats_tau_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    stats_tau_kernel<float><<<grid, warps * 32, smem, stream>>>((const float *)data, n_chains, L, c, out);
+  } else {
+    NK_CUDA_OK(cudaFuncSetAttribute(stats_tau_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    stats_tau_kernel<double><<<grid, warps * 32, smem, stream>>>((const double *)data, n_chains, L, c, out);
+  }
+  NK_LAUNCH_OK();
+  return NK_OK;
+}
+
 // Scalar arithmetic of _statistics (mc_stats_old.py:87-196) from globally reduced sums.
 int stats_finalize(const double *p, double mean, int64_t n_chains, int64_t L, double *out) {
   const double nan = NAN;

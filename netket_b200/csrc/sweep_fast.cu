@@ -83,6 +83,9 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 #ifndef NK_FAST_WARPS
 #define NK_FAST_WARPS 28
 #endif
+#ifndef NK_FAST_PREFETCH
+#define NK_FAST_PREFETCH 1  // 0: none, 1: the next proposal's record, 2: record and table row
+#endif
 constexpr int FAST_WARPS = NK_FAST_WARPS;
 constexpr int FAST_THREADS = FAST_WARPS * 32;
 constexpr float EXP_RANGE = 120.0f;      // log2 headroom allowed for a lane product
@@ -166,7 +169,7 @@ __host__ __device__ inline size_t fast_smem_bytes(int N, int MP, int E) {
   size_t s = (size_t)N * MP * 4;            // G table
   s += (size_t)N * 16;                      // per-site constants {x = log2e 2 sum_j W_ij, y = log2e 2 a_i, fix(x), fix(y)}
   s += ((size_t)2 * E + 15) & ~(size_t)15;  // edges (uint8 pairs)
-  s += (size_t)FAST_WARPS * 512;            // proposal records of the current batch, per warp
+  s += (size_t)FAST_WARPS * 512 + 16;       // proposal records of the current batch, per warp (+1: prefetch past the end)
   s += (size_t)FAST_WARPS * SIG_STRIDE;     // spins of the warp's chain (bytes, 1 = spin down)
   s += (size_t)FAST_WARPS * WSTAT * 8;      // statistics scratch per warp
   s += 16 + 32 * 4;                         // mbarrier, reduction scratch
@@ -240,7 +243,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1)
   float4 *rctab = reinterpret_cast<float4 *>(Gtab + (size_t)N * MP);
   uint8_t *edges = reinterpret_cast<uint8_t *>(rctab + N);
   uint4 *rectab = reinterpret_cast<uint4 *>(edges + (((size_t)2 * E + 15) & ~(size_t)15));
-  uint8_t *sigtab = reinterpret_cast<uint8_t *>(rectab + FAST_WARPS * 32);
+  uint8_t *sigtab = reinterpret_cast<uint8_t *>(rectab + FAST_WARPS * 32 + 1);
   double *wstat = reinterpret_cast<double *>(sigtab + FAST_WARPS * SIG_STRIDE);
   uint64_t *bar = reinterpret_cast<uint64_t *>(wstat + FAST_WARPS * WSTAT);
   float *red = reinterpret_cast<float *>(bar + 2);
@@ -447,12 +450,38 @@ __global__ void __launch_bounds__(FAST_THREADS, 1)
         // a segment = proposals up to the end of the sweep / of this batch
         const int kend = k + min(nb - k, sweep_size - in_sweep);
         in_sweep += kend - k;
+#if NK_FAST_PREFETCH >= 1
+        uint4 rec_n = lds128u(rec_s + 16u * k);
+#endif
+#if NK_FAST_PREFETCH >= 2
+        float2 g2_n[NPA];
+        float gt_n = 1.0f;
+        LM::load_row(rec_n.x + lane16, rec_n.x + tailoff, g2_n, gt_n);
+#endif
         for (; k < kend; ++k) {
+#if NK_FAST_PREFETCH >= 1
+          // the next proposal's record (and row) are in flight while this one is decided; past the batch's last record the
+          // load reads a neighbouring record that is never used
+          const uint4 rec = rec_n;
+#if NK_FAST_PREFETCH >= 2
+          rec_n = lds128u(rec_s + 16u * min(k + 1, 31));  // its row address is dereferenced: stay inside this warp's records
+#else
+          rec_n = lds128u(rec_s + 16u * (k + 1));
+#endif
+#else
           const uint4 rec = lds128u(rec_s + 16u * k);
+#endif
           const uint32_t sdown = lds_u8(rec.y);
           float2 g2[NPA];
           float gt = 1.0f;
+#if NK_FAST_PREFETCH >= 2
+#pragma unroll
+          for (int q = 0; q < NPA; ++q) g2[q] = g2_n[q];
+          gt = gt_n;
+          LM::load_row(rec_n.x + lane16, rec_n.x + tailoff, g2_n, gt_n);
+#else
           LM::load_row(rec.x + lane16, rec.x + tailoff, g2, gt);
+#endif
           // spin down (nu = +1): prod (B g + A), accept B <- B g;   spin up (nu = -1): prod (A g + B), accept A <- A g
           if (sdown) {
             const float P = lane_product<NP2, NPA, HAS_T>(c.B2, c.Bt, c.A2, c.At, g2, gt);

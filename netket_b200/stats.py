@@ -81,10 +81,100 @@ def finalize(sums, mean, n_chains_total, L):
     return Stats(out[0], out[1], out[2], out[3], out[4])
 
 
+def _allreduce_max_bits(t):
+    """MAX over ranks of order-preserving integer encodings (nk_stats_tau's out[1]) viewed as int64."""
+    _, ws = world()
+    if ws > 1:
+        v = t.view(torch.int64)
+        # the encoding is an unsigned order; flipping the top bit makes it the signed order int64 MAX uses
+        v ^= -0x8000000000000000
+        if dist.get_backend() == "gloo" and t.is_cuda:
+            c = v.cpu()
+            dist.all_reduce(c, op=dist.ReduceOp.MAX)
+            v.copy_(c)
+        else:
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        v ^= -0x8000000000000000
+    return t
+
+
+def statistics_fft(data):
+    """The opt-in FFT variant (netket/stats/mc_stats.py:303-331): mean / variance / R_hat as in the block version, error of the
+    mean from the chain means (from blocks for a single chain) whatever the quality flags, ``tau_corr`` = chain average of the
+    integrated autocorrelation time with Sokal's window (netket/stats/_autocorr.py:40-86), plus ``tau_corr_max``."""
+    data = _as_stats_input(data)
+    n_chains, L = data.shape
+    dev = data.device
+    code = _lib.dtype_code(data.dtype)
+    part = torch.zeros(_lib.NK_STATS_NPARTIAL, dtype=torch.float64, device=dev)
+    tau = torch.zeros(4, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        st = _lib.stream_ptr(dev)
+        _lib.check(_lib.lib().nk_stats_partial(st, _lib.ptr(data), code, n_chains, L, 0, 0.0, _lib.ptr(part)))
+        head = torch.cat([part[:1], torch.tensor([float(n_chains)], dtype=torch.float64, device=dev)])
+        _allreduce(head)
+        total, n_chains_total = head.tolist()
+        n_chains_total = int(round(n_chains_total))
+        mean = total / (n_chains_total * L)
+        _lib.check(_lib.lib().nk_stats_partial(st, _lib.ptr(data), code, n_chains, L, 1, mean, _lib.ptr(part)))
+        _lib.check(_lib.lib().nk_stats_tau(st, _lib.ptr(data), code, n_chains, L, 5.0, _lib.ptr(tau)))
+        _allreduce(part)
+        sums = torch.stack([tau[0], tau[2]])
+        _allreduce(sums)
+        _allreduce_max_bits(tau[1:2])
+    p = part.tolist()
+    tau_sum, n_nan = sums.tolist()
+    tau_max = float(_lib.lib().nk_stats_tau_max_decode(float(tau[1].item())))
+    ts = float(n_chains_total * L)
+    dm = p[7] / ts
+    variance = p[0] / ts - dm * dm
+    nan = math.nan
+    if n_chains_total > 1:
+        nb = float(n_chains_total)
+        batch_var = p[2] / nb - (p[1] / nb) ** 2
+        err = math.sqrt(max(batch_var, 0.0) / nb)
+        half = L // 2
+        hv = (p[6] / (2 * nb) - (p[5] / (2 * nb)) ** 2) if half > 0 else nan
+        rhat = math.sqrt((L - 1.0) / L + hv / variance) if variance > 0 else nan
+    else:
+        l_block = max(1, L // 32)
+        n_blocks = n_chains_total * (L // l_block)
+        block_var = p[4] / n_blocks - (p[3] / n_blocks) ** 2
+        err = math.sqrt(max(block_var, 0.0) / n_blocks)
+        rhat = nan
+    if n_nan > 0:
+        tau_avg, tau_max = nan, nan
+    else:
+        tau_avg = tau_sum / n_chains_total
+    return Stats(mean + dm, err, variance, tau_avg, rhat, tau_max)
+
+
+def _as_stats_input(data):
+    if not isinstance(data, torch.Tensor):
+        from .utils import default_device
+
+        data = torch.from_numpy(np.ascontiguousarray(np.asarray(data))).to(default_device())
+    _lib.require_cuda(data, "data")
+    if data.ndim == 0:
+        data = data.reshape(1, 1)
+    elif data.ndim == 1:
+        data = data.reshape(1, -1)
+    elif data.ndim > 2:
+        raise NotImplementedError("Statistics are implemented only for ndim<=2")
+    if data.dtype not in (torch.float32, torch.float64):
+        raise TypeError("statistics: float32 / float64 data only (real-parameter RBM => real local energies)")
+    return data.contiguous()
+
+
 def statistics(data):
     """Statistics of ``data[n_chains, L]`` (or a 1-D time series) held on this rank's GPU.  Under
     torch.distributed the chains of all ranks are combined (chain axis sharded, as the reference does with its
-    mesh axis "S": netket/stats/mc_stats_old.py:96-107)."""
+    mesh axis "S": netket/stats/mc_stats_old.py:96-107).  With the flag ``netket_experimental_fft_autocorrelation``
+    (netket_b200.config) the FFT variant runs instead, as in netket/stats/mc_stats.py:296-301."""
+    from .config import config
+
+    if config.netket_experimental_fft_autocorrelation:
+        return statistics_fft(data)
     if not isinstance(data, torch.Tensor):
         from .utils import default_device
 

@@ -129,8 +129,7 @@ def test_cfg4_full_size_subsample_vs_oracle(cuda):
     ref_e = oest.local_value_kernel(conf, lambda x: oops.local_operator_conn_padded(x, tables), W, b, a)
     assert_rel(eloc[torch.from_numpy(cs).cuda(), torch.from_numpy(ts).cuda()].cpu().numpy(), ref_e, F64_TOL, "fused J1-J2 E_loc")
     ids = _spread(B, 36, 148 * 12, rs)
-    e1, _ = ograph.hypercube_edges(10, 2)
-    clusters = ograph.compute_clusters(100, e1, 1)
+    clusters = ograph.compute_clusters(100, e, 1)  # d_max = 1 on the J1-J2 graph: its 200 + 200 bonds
     assert np.array_equal(clusters, sa.rule.clusters)
     ref = _oracle_chains("exchange", st0.σ.cpu().numpy(), ids, W, b, a, seed, t0, ND + CL, 100, np.float64, clusters=clusters)
     assert np.array_equal(samples[torch.from_numpy(ids).cuda()].cpu().numpy(), ref["samples"][:, ND:])

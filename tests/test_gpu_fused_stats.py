@@ -127,3 +127,48 @@ def test_user_registered_operator_goes_through_the_multimethods(cuda):
     np.testing.assert_allclose(vs.expect(Twice(op)).mean, 2.0 * base.mean, rtol=1e-12)
     with pytest.raises(NotImplementedError):
         vs.expect(object())
+
+
+# ---------------------------------------------------------------------------------------------- FFT variant of `statistics`
+import os  # noqa: E402
+
+_GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "online_stats_vectors.npz"))
+
+
+@pytest.mark.parametrize("tag", [str(t) for t in _GOLD["fft_cases"]])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_fft_statistics_match_reference_vectors(cuda, tag, dtype):
+    """netket/stats/mc_stats.py:303-331 + _autocorr.py:40-86 executed from the reference's source (make_golden_online.py):
+    mean, error_of_mean, variance, tau_corr (Sokal window, chain average), R_hat, tau_corr_max."""
+    import netket_b200 as nk
+
+    data = _GOLD[f"{tag}_data"].astype(dtype)
+    want = _GOLD[f"{tag}_result"]
+    st = nk.stats.statistics_fft(torch.from_numpy(data).cuda())
+    got = np.array([st.mean, st.error_of_mean, st.variance, st.tau_corr, st.R_hat, st.tau_corr_max])
+    if dtype == np.float64:
+        np.testing.assert_allclose(got, want, rtol=1e-10, equal_nan=True)
+    else:
+        ref = oracle.stats.statistics_fft(data.astype(np.float64))  # the same rounded inputs, in double
+        want32 = np.array([ref[k] for k in ("mean", "error_of_mean", "variance", "tau_corr", "R_hat", "tau_corr_max")])
+        np.testing.assert_allclose(got, want32, rtol=1e-9, equal_nan=True)
+
+
+def test_statistics_flag_switches_to_the_fft_variant(cuda):
+    import netket_b200 as nk
+
+    rs = np.random.default_rng(3)
+    x = torch.from_numpy(rs.normal(size=(8, 64)).cumsum(axis=1) * 0.3).cuda()
+    plain = nk.stats.statistics(x)
+    assert np.isnan(plain.tau_corr_max)
+    nk.config.update("netket_experimental_fft_autocorrelation", True)
+    try:
+        fft = nk.stats.statistics(x)
+    finally:
+        nk.config.update("netket_experimental_fft_autocorrelation", False)
+    ref = oracle.stats.statistics_fft(x.cpu().numpy())
+    for k in ("mean", "error_of_mean", "variance", "tau_corr", "R_hat", "tau_corr_max"):
+        np.testing.assert_allclose(getattr(fft, k), ref[k], rtol=1e-10, err_msg=k)
+    # a constant chain has no autocorrelation function: tau is NaN, as jnp's 0 / 0
+    c = torch.ones((4, 16), dtype=torch.float64, device="cuda")
+    assert np.isnan(nk.stats.statistics_fft(c).tau_corr)
