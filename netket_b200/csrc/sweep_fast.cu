@@ -20,156 +20,35 @@
 // The binding resource is the shared-memory read of one G row (M floats) per proposal per chain.
 //
 // Proposal loop (v7).  The 32 proposals of a batch are prepared by the 32 lanes in parallel (Philox, site, threshold,
-// per-site constants) and left in a per-warp shared-memory record {row address, spin address, threshold - fix(x_i),
-// fix(y_i)}; a proposal then starts with ONE broadcast LDS.128 instead of three shuffles, the chain's spins live as
-// bytes in shared memory (one LDS.U8 to read, one STS.U8 on accept) and the whole accept test is integer:
+// per-site constants) and left in a per-warp shared-memory record {row address, earlier proposals of the batch on the same
+// site | spin at the start of the batch, threshold - fix(x_i), fix(y_i)}; a proposal then starts with ONE broadcast LDS.128
+// instead of three shuffles, takes its spin from the parity of the batch's accept mask (the chain's spin bytes in shared
+// memory are only touched once per batch and at sweep ends) and the whole accept test is integer:
 //   fix(log2 ratio) = (Rp - R) + fix(x_i) +- fix(y_i),   x_i = log2e 2 sum_j W_ij,  y_i = log2e 2 a_i,
 //   accept = u < exp(machine_pow * delta)  <=>  fix(log2(u) / machine_pow) < fix(log2 ratio)   (metropolis.py:444-450).
 //
 // Validity: 2 NP * (4 max|W| log2 e) <= 120 (|W| <~ 1.5 at 14 units per lane); otherwise the kernel raises a device flag and
 // the kernels enqueued behind it do the work without a host round trip: the general product-form kernel in its wide mode
 // (two logarithms per lane product, |W| <~ 3), then the theta-form kernel.
-#include "kernels.cuh"
+#include "fast_common.cuh"
 
 namespace nk {
 
-typedef unsigned long long u64;
-
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-  u64 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(*reinterpret_cast<u64 *>(&a)), "l"(*reinterpret_cast<u64 *>(&b)),
-      "l"(*reinterpret_cast<u64 *>(&c)));
-  return *reinterpret_cast<float2 *>(&d);
-}
-__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
-  u64 d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<u64 *>(&a)), "l"(*reinterpret_cast<u64 *>(&b)));
-  return *reinterpret_cast<float2 *>(&d);
-}
-__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
-  u64 d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<u64 *>(&a)), "l"(*reinterpret_cast<u64 *>(&b)));
-  return *reinterpret_cast<float2 *>(&d);
-}
-
-// ---- mbarrier / TMA bulk copy (global -> shared), PTX
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  uint32_t done = 0;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
+using namespace fast;
 
 #ifndef NK_FAST_WARPS
 #define NK_FAST_WARPS 28
 #endif
-#ifndef NK_FAST_PREFETCH
-#define NK_FAST_PREFETCH 1  // 0: none, 1: the next proposal's record, 2: record and table row
-#endif
 constexpr int FAST_WARPS = NK_FAST_WARPS;
 constexpr int FAST_THREADS = FAST_WARPS * 32;
-constexpr float EXP_RANGE = 120.0f;      // log2 headroom allowed for a lane product
-constexpr float FX_SCALE = 524288.0f;    // 2^19: fixed-point scale of per-lane log2 partials (REDUX add)
-constexpr int THR_MIN = -(1 << 29);      // "always accept" threshold (u == 0 or machine_pow == 0): -1024 in log2 units
 constexpr int SIG_STRIDE = 128;          // spin bytes per warp (N <= 128)
 constexpr int WSTAT = 12;                // doubles of statistics scratch per warp
-
-// ---- explicit shared-space accesses (32-bit shared addresses kept in registers; no generic-address arithmetic)
-__device__ __forceinline__ float4 lds128(uint32_t a) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ uint4 lds128u(uint32_t a) {
-  uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ void sts128u(uint32_t a, uint4 v) {
-  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ float2 lds64(uint32_t a) {
-  float2 v;
-  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ float lds32(uint32_t a) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
-  uint32_t v;
-  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ float lg2_fast(float x) {  // x is a positive normal number by construction
-  float y;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float ex2_fast(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float rcp_fast(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-// A lane owns NE = 4 NFULL + TAIL hidden units: NP2 float2 pairs (FFMA2 / FMUL2) plus, for TAIL == 1, one scalar.
-template <int NFULL, int TAIL>
-struct Lanes {
-  static constexpr int NE = 4 * NFULL + TAIL;                      // hidden units per lane
-  static constexpr int NP2 = 2 * NFULL + (TAIL == 2 ? 1 : 0);      // float2 pairs per lane
-  static constexpr int NPA = NP2 > 0 ? NP2 : 1;                    // array extent (no zero-sized arrays)
-  static constexpr bool HAS_T = TAIL == 1;                         // odd unit carried as a scalar
-  static constexpr int MP = 128 * NFULL + 32 * TAIL;               // padded row length of the G table (floats)
-  // hidden-unit index of element e of this lane (may be >= M: padding)
-  static __device__ __forceinline__ int unit(int e, int lane) {
-    return e < 4 * NFULL ? 128 * (e >> 2) + 4 * lane + (e & 3) : 128 * NFULL + TAIL * lane + (e - 4 * NFULL);
-  }
-  // row_lane = shared address of G[i][0] + 16 * lane ; tail_lane = shared address of G[i][128*NFULL + TAIL*lane]
-  static __device__ __forceinline__ void load_row(uint32_t row_lane, uint32_t tail_lane, float2 (&g2)[NPA], float &gt) {
-#pragma unroll
-    for (int q = 0; q < NFULL; ++q) {
-      const float4 v = lds128(row_lane + 512 * q);
-      g2[2 * q] = make_float2(v.x, v.y);
-      g2[2 * q + 1] = make_float2(v.z, v.w);
-    }
-    if (TAIL == 1) gt = lds32(tail_lane);
-    if (TAIL == 2) g2[2 * NFULL] = lds64(tail_lane);
-  }
-};
 
 __host__ __device__ inline size_t fast_smem_bytes(int N, int MP, int E) {
   size_t s = (size_t)N * MP * 4;            // G table
   s += (size_t)N * 16;                      // per-site constants {x = log2e 2 sum_j W_ij, y = log2e 2 a_i, fix(x), fix(y)}
   s += ((size_t)2 * E + 15) & ~(size_t)15;  // edges (uint8 pairs)
-  s += (size_t)FAST_WARPS * 512 + 16;       // proposal records of the current batch, per warp (+1: prefetch past the end)
+  s += (size_t)FAST_WARPS * 512;            // proposal records of the current batch, per warp
   s += (size_t)FAST_WARPS * SIG_STRIDE;     // spins of the warp's chain (bytes, 1 = spin down)
   s += (size_t)FAST_WARPS * WSTAT * 8;      // statistics scratch per warp
   s += 16 + 32 * 4;                         // mbarrier, reduction scratch
@@ -178,57 +57,6 @@ __host__ __device__ inline size_t fast_smem_bytes(int N, int MP, int E) {
 
 __device__ __forceinline__ uint32_t sw4sel(const uint32_t (&w)[4], int i) {
   return (i < 2) ? ((i == 0) ? w[0] : w[1]) : ((i == 2) ? w[2] : w[3]);
-}
-
-// Per-chain registers of one warp.
-template <int NPA>
-struct ChainRegs {
-  float2 A2[NPA], B2[NPA];
-  float At, Bt;          // the scalar unit (TAIL == 1)
-  int R;                 // fixed-point log2 prod_j (A_j + B_j), summed over the warp
-  uint32_t nacc;         // accepted moves of this call
-  uint32_t next_renorm;  // renormalise when nacc reaches this
-};
-
-// lane product prod_j (X_j g_j + Y_j) over the lane's units
-template <int NP2, int NPA, bool HAS_T>
-__device__ __forceinline__ float lane_product(const float2 (&X)[NPA], float Xt, const float2 (&Y)[NPA], float Yt, const float2 (&g2)[NPA],
-                                              float gt) {
-  float P = 1.0f;
-  if (NP2 > 0) {
-    float2 Pa = ffma2(X[0], g2[0], Y[0]);
-    float2 Pb = make_float2(1.0f, 1.0f);
-    if (NP2 > 1) Pb = ffma2(X[1], g2[1], Y[1]);
-#pragma unroll
-    for (int q = 2; q < NP2; ++q) {
-      const float2 c = ffma2(X[q], g2[q], Y[q]);
-      if (q & 1)
-        Pb = fmul2(Pb, c);
-      else
-        Pa = fmul2(Pa, c);
-    }
-    if (NP2 > 1) Pa = fmul2(Pa, Pb);
-    P = Pa.x * Pa.y;
-  }
-  if (HAS_T) {
-    const float ct = fmaf(Xt, gt, Yt);
-    P = NP2 > 0 ? P * ct : ct;
-  }
-  return P;
-}
-
-// fixed-point log2 prod_j (A_j + B_j), summed over the warp
-template <int NP2, int NPA, bool HAS_T>
-__device__ __forceinline__ float lane_norm(const ChainRegs<NPA> &c) {
-  float P = 1.0f;
-  if (NP2 > 0) {
-    float2 Pa = fadd2(c.A2[0], c.B2[0]);
-#pragma unroll
-    for (int q = 1; q < NP2; ++q) Pa = fmul2(Pa, fadd2(c.A2[q], c.B2[q]));
-    P = Pa.x * Pa.y;
-  }
-  if (HAS_T) P *= c.At + c.Bt;
-  return P;
 }
 
 template <int NFULL, int TAIL>
@@ -243,7 +71,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1)
   float4 *rctab = reinterpret_cast<float4 *>(Gtab + (size_t)N * MP);
   uint8_t *edges = reinterpret_cast<uint8_t *>(rctab + N);
   uint4 *rectab = reinterpret_cast<uint4 *>(edges + (((size_t)2 * E + 15) & ~(size_t)15));
-  uint8_t *sigtab = reinterpret_cast<uint8_t *>(rectab + FAST_WARPS * 32 + 1);
+  uint8_t *sigtab = reinterpret_cast<uint8_t *>(rectab + FAST_WARPS * 32);
   double *wstat = reinterpret_cast<double *>(sigtab + FAST_WARPS * SIG_STRIDE);
   uint64_t *bar = reinterpret_cast<uint64_t *>(wstat + FAST_WARPS * WSTAT);
   float *red = reinterpret_cast<float *>(bar + 2);
@@ -435,53 +263,44 @@ __global__ void __launch_bounds__(FAST_THREADS, 1)
           thr_l = __float2int_rn(fmaxf(t2, (float)THR_MIN));
         }
         const float4 rc = lds128(rc_s + 16u * site_l);
+        // spins inside a batch: the record carries the spin at the start of the batch (bit 31) and the earlier proposals of
+        // this batch on the same site (bits 0..30); the spin a proposal sees is their parity with the accept mask, so the
+        // loop neither reads nor writes the spin bytes (2 of 16 shared-memory wavefronts per proposal saved)
+        const uint32_t peers = __match_any_sync(0xffffffffu, site_l);
         uint4 rec;
         rec.x = g_s + (uint32_t)site_l * (uint32_t)(MP * 4);
-        rec.y = sig_s + (uint32_t)site_l;
+        rec.y = (peers & ((1u << lane_o) - 1u)) | (lds_u8(sig_s + (uint32_t)site_l) << 31);
         rec.z = (uint32_t)thr_l - (uint32_t)__float_as_int(rc.z);
         rec.w = (uint32_t)__float_as_int(rc.w);
         __syncwarp();
         sts128u(rec_s + 16u * lane_o, rec);
         __syncwarp();
       }
+      uint32_t accmask = 0;  // bit k: proposal k of this batch was accepted
+      // spin bytes <- the spins after the first `upto` proposals of this batch (the last executed proposal of a site writes)
+      auto flush = [&](const int upto) {
+        const uint4 own = lds128u(rec_s + 16u * lane_o);
+        const uint32_t site = (own.x - g_s) / (uint32_t)(MP * 4);
+        const uint32_t valid = upto >= 32 ? 0xffffffffu : ((1u << upto) - 1u);
+        const uint32_t peers = __match_any_sync(0xffffffffu, site) & valid;
+        if (((valid >> lane_o) & 1u) && (peers >> lane_o) == 1u) {
+          const uint32_t pre = __popc(own.y & (accmask | 0x80000000u)) & 1u;
+          sts_u8(sig_s + site, pre ^ ((accmask >> lane_o) & 1u));
+        }
+        __syncwarp();
+      };
       const int nb = min(32, T_total - tt);
       int k = 0;
       while (k < nb) {
         // a segment = proposals up to the end of the sweep / of this batch
         const int kend = k + min(nb - k, sweep_size - in_sweep);
         in_sweep += kend - k;
-#if NK_FAST_PREFETCH >= 1
-        uint4 rec_n = lds128u(rec_s + 16u * k);
-#endif
-#if NK_FAST_PREFETCH >= 2
-        float2 g2_n[NPA];
-        float gt_n = 1.0f;
-        LM::load_row(rec_n.x + lane16, rec_n.x + tailoff, g2_n, gt_n);
-#endif
         for (; k < kend; ++k) {
-#if NK_FAST_PREFETCH >= 1
-          // the next proposal's record (and row) are in flight while this one is decided; past the batch's last record the
-          // load reads a neighbouring record that is never used
-          const uint4 rec = rec_n;
-#if NK_FAST_PREFETCH >= 2
-          rec_n = lds128u(rec_s + 16u * min(k + 1, 31));  // its row address is dereferenced: stay inside this warp's records
-#else
-          rec_n = lds128u(rec_s + 16u * (k + 1));
-#endif
-#else
           const uint4 rec = lds128u(rec_s + 16u * k);
-#endif
-          const uint32_t sdown = lds_u8(rec.y);
+          const uint32_t sdown = __popc(rec.y & (accmask | 0x80000000u)) & 1u;
           float2 g2[NPA];
           float gt = 1.0f;
-#if NK_FAST_PREFETCH >= 2
-#pragma unroll
-          for (int q = 0; q < NPA; ++q) g2[q] = g2_n[q];
-          gt = gt_n;
-          LM::load_row(rec_n.x + lane16, rec_n.x + tailoff, g2_n, gt_n);
-#else
           LM::load_row(rec.x + lane16, rec.x + tailoff, g2, gt);
-#endif
           // spin down (nu = +1): prod (B g + A), accept B <- B g;   spin up (nu = -1): prod (A g + B), accept A <- A g
           if (sdown) {
             const float P = lane_product<NP2, NPA, HAS_T>(c.B2, c.Bt, c.A2, c.At, g2, gt);
@@ -491,7 +310,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1)
               for (int q = 0; q < NP2; ++q) c.B2[q] = fmul2(c.B2[q], g2[q]);
               if (HAS_T) c.Bt *= gt;
               c.R = Rp;
-              sts_u8(rec.y, 0u);
+              accmask |= 1u << k;
               if (++c.nacc == c.next_renorm) renormalise();
             }
           } else {
@@ -502,11 +321,12 @@ __global__ void __launch_bounds__(FAST_THREADS, 1)
               for (int q = 0; q < NP2; ++q) c.A2[q] = fmul2(c.A2[q], g2[q]);
               if (HAS_T) c.At *= gt;
               c.R = Rp;
-              sts_u8(rec.y, 1u);
+              accmask |= 1u << k;
               if (++c.nacc == c.next_renorm) renormalise();
             }
           }
         }
+        flush(kend);
         if (in_sweep == sweep_size) {
           in_sweep = 0;
           const int sw = sweep_idx - p.n_discard;

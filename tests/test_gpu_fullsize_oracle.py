@@ -18,6 +18,7 @@ from oracle import operators as oops
 from oracle import rbm as orbm
 from oracle import rng as orng
 from oracle import sampler as osampler
+from tolerances import assert_rel, f32_tol, record, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -36,12 +37,6 @@ def _var(N, alpha, dtype, std=0.01, seed=1234):
     var = {"params": {"Dense": {"kernel": torch.from_numpy(W).cuda(), "bias": torch.from_numpy(b).cuda()},
                       "visible_bias": torch.from_numpy(a).cuda()}}
     return (W.astype(np.float64), b.astype(np.float64), a.astype(np.float64)), var
-
-
-def assert_rel(x, ref, tol, what=""):
-    """Element-wise relative error; values below 1 % of the largest magnitude are held to an absolute floor of tol * 1 % * max."""
-    x, ref = np.asarray(x, dtype=np.float64), np.asarray(ref, dtype=np.float64)
-    np.testing.assert_allclose(x, ref, rtol=tol, atol=tol * 0.01 * np.abs(ref).max(), err_msg=what)
 
 
 def _spread(B, n, slots, rs):
@@ -161,7 +156,11 @@ def test_cfg5_instantiation_vs_oracle(cuda, dtype):
         assert_rel(eloc.cpu().numpy(), ref_e, F64_TOL, "cfg-5 E_loc fp64")
     else:
         assert _check_fp32_chains(got, ref, 0, 400) >= 0.8
-        assert_rel(eloc.cpu().numpy(), ref_e, F32_TOL, "cfg-5 E_loc fp32")
+        assert_rel(eloc.cpu().numpy(), ref_e, f32_tol(3200), "cfg-5 E_loc fp32")
+        # the reference algorithm itself in float32 (NumPy) on the same samples: its own distance from the float64 values
+        W32, b32, a32 = (x.astype(np.float32) for x in (W, b, a))
+        ref32 = oest.local_estimators(got[:8], lambda x: oops.ising_conn_padded(x, e, 3.0, 1.0), W32, b32, a32)
+        record("cfg-5 E_loc: reference algorithm in float32 vs float64 oracle", f32_tol(3200), rel_err(ref32, ref_e[:8], 0.1))
     # the stand-alone estimator takes the same kernel family (theta GEMM for N > 128 / M > 512, then the E_loc code)
     vs = nk.vqs.MCState(sa, model, variables=var, n_samples=B, seed=1)
-    assert_rel(vs._eloc_on_samples(op, samples).cpu().numpy(), ref_e, F64_TOL if dtype == np.float64 else F32_TOL, "stand-alone")
+    assert_rel(vs._eloc_on_samples(op, samples).cpu().numpy(), ref_e, F64_TOL if dtype == np.float64 else f32_tol(3200), "stand-alone")

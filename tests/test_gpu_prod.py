@@ -17,7 +17,7 @@ from oracle import operators as oops
 from oracle import rbm as orbm
 from oracle import rng as orng
 from oracle import sampler as osampler
-from tolerances import F32_TOL, F32_TOL_LARGE_W, F64_TOL, assert_rel
+from tolerances import F32_TOL, F32_TOL_LARGE_W, F64_TOL, assert_rel, f32_tol, record, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -363,8 +363,11 @@ def test_prod_large_fused_eloc(cuda, dtype, rule, L, n_dim, alpha, std, total_sz
     st = sa.init_state(model, var, seed=11)
     samples, _, eloc, st2 = sa._launch(model, var, st, 2, n_discard=1, operator=op, path=PROD)
     ref = oest.local_estimators(samples.cpu().numpy(), conn, *_f64(W, b, a))
-    tol = F64_TOL if dtype == np.float64 else F32_TOL
+    tol = F64_TOL if dtype == np.float64 else f32_tol(W.shape[1])
     assert_rel(eloc.cpu().numpy(), ref, tol)
+    if dtype == np.float32 and W.shape[1] > 512:  # the reference algorithm itself in float32 (NumPy): its own rounding error
+        ref32 = oest.local_estimators(samples.cpu().numpy()[:6], conn, W, b, a)
+        record("reference algorithm in float32 vs float64 oracle, M = %d" % W.shape[1], tol, rel_err(ref32, ref[:6], 0.1))
     # fp32: the chain itself follows the oracle's up to accept-boundary ties
     if dtype == np.float32:
         seed, t0 = st.rng

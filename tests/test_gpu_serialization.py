@@ -28,7 +28,8 @@ def test_mcstate_round_trip_resumes_the_same_chains(cuda):
     vs.reset()
     sd = pickle.loads(pickle.dumps(vs.to_state_dict()))  # plain dicts of NumPy arrays / Python scalars
     assert set(sd) == {"variables", "sampler_state", "n_samples", "n_discard_per_chain", "chunk_size"}
-    assert set(sd["sampler_state"]) == {"σ", "rng", "n_steps_proc", "n_accepted_proc"}  # log_prob is not serialised
+    # the reference's keys (metropolis.py:50-74): log_prob is not serialised, rule_state is (None for these rules)
+    assert set(sd["sampler_state"]) == {"σ", "rng", "rule_state", "n_steps_proc", "n_accepted_proc"}
     assert sd["sampler_state"]["σ"].dtype == np.int8 and sd["sampler_state"]["rng"].dtype == np.uint64
     e1 = vs.expect(op)
     s1 = vs.samples.clone()
