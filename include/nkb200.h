@@ -103,6 +103,12 @@ typedef struct nk_chains_t {
   uint64_t chain_offset; /* global index of chain 0 of this device (multi-GPU sharding) */
 } nk_chains_t;
 
+/* nk_sweep_t.flags */
+#define NK_SWEEP_NO_HANDOVER 1 /* enqueue ONLY the tuned kernel NK_PATH_AUTO would try first (fewer launches per step).  If the
+                                  weights turn out to be outside that kernel's numerical range nothing is sampled and, with
+                                  stats_out given, stats_out[0] is NaN: the caller, who reads the sums anyway, repeats the call
+                                  without this flag (the chain state was not touched).  Needs stats_out. */
+
 typedef struct nk_sweep_t {
   int32_t rule;         /* NK_RULE_* */
   int32_t chain_length; /* recorded sweeps */
@@ -124,7 +130,7 @@ typedef struct nk_sweep_t {
   const nk_localop_t *localop; /* or NULL */
   void *eloc_out;              /* [B, chain_length] */
   int32_t eloc_dtype;          /* NK_F32 | NK_F64 = promote(operator dtype, rbm dtype) */
-  int32_t reserved;
+  int32_t flags;               /* NK_SWEEP_* bits */
   /* optional: tanh(theta) of every recorded sample, [B, chain_length, M] in the rbm dtype.  The sweep kernels hold it in
    * registers anyway ((A - B) / (A + B)); nk_forces_rbm takes it instead of recomputing theta for the whole batch */
   void *tanh_out;

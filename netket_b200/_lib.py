@@ -61,7 +61,7 @@ class nk_sweep_t(C.Structure):
                 ("machine_pow", C.c_double), ("samples_out", C.c_void_p), ("logp_out", C.c_void_p),
                 ("stream_w0", C.c_void_p), ("stream_u", C.c_void_p), ("clusters", C.c_void_p), ("n_clusters", C.c_int32),
                 ("path", C.c_int32), ("ising", C.POINTER(nk_ising_t)), ("localop", C.POINTER(nk_localop_t)),
-                ("eloc_out", C.c_void_p), ("eloc_dtype", C.c_int32), ("reserved", C.c_int32), ("tanh_out", C.c_void_p),
+                ("eloc_out", C.c_void_p), ("eloc_dtype", C.c_int32), ("flags", C.c_int32), ("tanh_out", C.c_void_p),
                 ("stats_out", C.c_void_p), ("stats_shift", C.c_double), ("cluster_probs", C.c_void_p)]
 
 
@@ -74,6 +74,7 @@ class nk_ctx_desc_t(C.Structure):
                 ("eloc_in_param_dtype", C.c_int32), ("reserved", C.c_int32)]
 
 
+NK_SWEEP_NO_HANDOVER = 1
 NK_CTX_NPARTIAL = NK_STATS_NPARTIAL + 2
 NK_RESHIFT = 1
 

@@ -169,6 +169,7 @@ int nk_sweep(void *stream, const nk_rbm_t *rbm, nk_chains_t *ch, const nk_sweep_
   }
   NK_CHECK_ARG(a->path >= NK_PATH_AUTO && a->path <= NK_PATH_PROD, "nk_sweep: bad path %d", a->path);
   NK_CHECK_ARG(a->stats_out == nullptr || a->ising || a->localop, "nk_sweep: stats_out needs a fused operator (ising / localop)");
+  NK_CHECK_ARG(!(a->flags & NK_SWEEP_NO_HANDOVER) || a->stats_out != nullptr, "nk_sweep: NK_SWEEP_NO_HANDOVER needs stats_out");
   if (a->stats_out) NK_CUDA_OK(cudaMemsetAsync(a->stats_out, 0, sizeof(double) * NK_STATS_NPARTIAL, (cudaStream_t)stream));
   if (ch->B == 0) return NK_OK;
 
@@ -201,6 +202,7 @@ int nk_sweep(void *stream, const nk_rbm_t *rbm, nk_chains_t *ch, const nk_sweep_
   k.stats_out = a->stats_out;
   k.stats_shift = a->stats_shift;
   k.cluster_probs = a->rule == NK_RULE_EXCHANGE ? a->cluster_probs : nullptr;
+  k.no_handover = (a->flags & NK_SWEEP_NO_HANDOVER) ? 1 : 0;
   const int *stats_guard = nullptr;  // the tuned fp32 kernel reduces its energies itself; the other kernels leave it to K6
 
   // path selection: the tuned fp32 LocalRule kernel (sweep_fast) where it applies, the general product-form kernel
@@ -231,6 +233,11 @@ int nk_sweep(void *stream, const nk_rbm_t *rbm, nk_chains_t *ch, const nk_sweep_
       // in-stream, and only if that gives up as well (flags[5]) the theta-form kernel runs
       rc = sweep_fast(st, k, reinterpret_cast<const float *>(theta), flags);
       stats_guard = flags;  // flags[0] != 0: the tuned kernel handed over without producing anything
+      if (a->flags & NK_SWEEP_NO_HANDOVER) {
+        // the caller takes the hand-over on itself (stats_out[0] = NaN tells it): no guarded launches behind the tuned kernel
+        if (rc == NK_OK) ch->t += (uint64_t)(a->n_discard + a->chain_length) * (uint64_t)a->sweep_size;
+        return rc;
+      }
       if (rc == NK_OK && a->path != NK_PATH_FAST && sweep_prod_supported(k)) {
         rc = sweep_prod(st, k, theta, flags, tables, flags, 5);
         guard = flags + 5;

@@ -37,6 +37,7 @@ struct SweepKernelArgs {
   double *stats_out;
   double stats_shift;
   const double *cluster_probs;  // ExchangeRule(probabilities=): [n_clusters] weights, or NULL (uniform)
+  int32_t no_handover;          // NK_SWEEP_NO_HANDOVER: a kernel that gives up writes NaN into stats_out[0]
 };
 
 // sweep_generic.cu — theta-form path (any shape / dtype / rule)

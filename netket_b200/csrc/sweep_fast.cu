@@ -20,10 +20,9 @@
 // The binding resource is the shared-memory read of one G row (M floats) per proposal per chain.
 //
 // Proposal loop (v7).  The 32 proposals of a batch are prepared by the 32 lanes in parallel (Philox, site, threshold,
-// per-site constants) and left in a per-warp shared-memory record {row address, earlier proposals of the batch on the same
-// site | spin at the start of the batch, threshold - fix(x_i), fix(y_i)}; a proposal then starts with ONE broadcast LDS.128
-// instead of three shuffles, takes its spin from the parity of the batch's accept mask (the chain's spin bytes in shared
-// memory are only touched once per batch and at sweep ends) and the whole accept test is integer:
+// per-site constants) and left in a per-warp shared-memory record {row address, spin address, threshold - fix(x_i),
+// fix(y_i)}; a proposal then starts with ONE broadcast LDS.128 instead of three shuffles, the chain's spins live as
+// bytes in shared memory (one LDS.U8 to read, one STS.U8 on accept) and the whole accept test is integer:
 //   fix(log2 ratio) = (Rp - R) + fix(x_i) +- fix(y_i),   x_i = log2e 2 sum_j W_ij,  y_i = log2e 2 a_i,
 //   accept = u < exp(machine_pow * delta)  <=>  fix(log2(u) / machine_pow) < fix(log2 ratio)   (metropolis.py:444-450).
 //
@@ -133,7 +132,10 @@ __global__ void __launch_bounds__(FAST_THREADS, 1)
     if (!(wmax < 1.0e30f)) renorm = 0;  // NaN / Inf weights
   }
   if (renorm < 1) {  // weights too large for the product form: hand over to the generic kernel queued behind us
-    if (blockIdx.x == 0 && tid == 0) flags[0] = 1;
+    if (blockIdx.x == 0 && tid == 0) {
+      flags[0] = 1;
+      if (p.no_handover && p.stats_out != nullptr) p.stats_out[0] = __longlong_as_double(0x7ff8000000000000ll);  // NaN: NK_SWEEP_NO_HANDOVER callers repeat the call
+    }
     return;
   }
 
@@ -263,32 +265,15 @@ __global__ void __launch_bounds__(FAST_THREADS, 1)
           thr_l = __float2int_rn(fmaxf(t2, (float)THR_MIN));
         }
         const float4 rc = lds128(rc_s + 16u * site_l);
-        // spins inside a batch: the record carries the spin at the start of the batch (bit 31) and the earlier proposals of
-        // this batch on the same site (bits 0..30); the spin a proposal sees is their parity with the accept mask, so the
-        // loop neither reads nor writes the spin bytes (2 of 16 shared-memory wavefronts per proposal saved)
-        const uint32_t peers = __match_any_sync(0xffffffffu, site_l);
         uint4 rec;
         rec.x = g_s + (uint32_t)site_l * (uint32_t)(MP * 4);
-        rec.y = (peers & ((1u << lane_o) - 1u)) | (lds_u8(sig_s + (uint32_t)site_l) << 31);
+        rec.y = sig_s + (uint32_t)site_l;
         rec.z = (uint32_t)thr_l - (uint32_t)__float_as_int(rc.z);
         rec.w = (uint32_t)__float_as_int(rc.w);
         __syncwarp();
         sts128u(rec_s + 16u * lane_o, rec);
         __syncwarp();
       }
-      uint32_t accmask = 0;  // bit k: proposal k of this batch was accepted
-      // spin bytes <- the spins after the first `upto` proposals of this batch (the last executed proposal of a site writes)
-      auto flush = [&](const int upto) {
-        const uint4 own = lds128u(rec_s + 16u * lane_o);
-        const uint32_t site = (own.x - g_s) / (uint32_t)(MP * 4);
-        const uint32_t valid = upto >= 32 ? 0xffffffffu : ((1u << upto) - 1u);
-        const uint32_t peers = __match_any_sync(0xffffffffu, site) & valid;
-        if (((valid >> lane_o) & 1u) && (peers >> lane_o) == 1u) {
-          const uint32_t pre = __popc(own.y & (accmask | 0x80000000u)) & 1u;
-          sts_u8(sig_s + site, pre ^ ((accmask >> lane_o) & 1u));
-        }
-        __syncwarp();
-      };
       const int nb = min(32, T_total - tt);
       int k = 0;
       while (k < nb) {
@@ -297,7 +282,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1)
         in_sweep += kend - k;
         for (; k < kend; ++k) {
           const uint4 rec = lds128u(rec_s + 16u * k);
-          const uint32_t sdown = __popc(rec.y & (accmask | 0x80000000u)) & 1u;
+          const uint32_t sdown = lds_u8(rec.y);
           float2 g2[NPA];
           float gt = 1.0f;
           LM::load_row(rec.x + lane16, rec.x + tailoff, g2, gt);
@@ -310,7 +295,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1)
               for (int q = 0; q < NP2; ++q) c.B2[q] = fmul2(c.B2[q], g2[q]);
               if (HAS_T) c.Bt *= gt;
               c.R = Rp;
-              accmask |= 1u << k;
+              sts_u8(rec.y, 0u);
               if (++c.nacc == c.next_renorm) renormalise();
             }
           } else {
@@ -321,12 +306,11 @@ __global__ void __launch_bounds__(FAST_THREADS, 1)
               for (int q = 0; q < NP2; ++q) c.A2[q] = fmul2(c.A2[q], g2[q]);
               if (HAS_T) c.At *= gt;
               c.R = Rp;
-              accmask |= 1u << k;
+              sts_u8(rec.y, 1u);
               if (++c.nacc == c.next_renorm) renormalise();
             }
           }
         }
-        flush(kend);
         if (in_sweep == sweep_size) {
           in_sweep = 0;
           const int sw = sweep_idx - p.n_discard;

@@ -261,7 +261,8 @@ class MetropolisSampler:
         return state.replace(σ=sigma, log_prob=log_prob, n_steps_proc=0, n_accepted_proc=torch.zeros_like(state.n_accepted_proc))
 
     def _launch(self, machine, parameters, state, chain_length, *, n_discard=0, return_log_probabilities=False,
-                operator=None, stream=None, path=_lib.NK_PATH_AUTO, want_samples=True, tanh_out=None, stats_shift=None):
+                operator=None, stream=None, path=_lib.NK_PATH_AUTO, want_samples=True, tanh_out=None, stats_shift=None,
+                no_handover=False):
         """One ``nk_sweep`` call.  Returns (samples, logp|None, eloc|None, new_state).  ``tanh_out``: optional tensor
         ``(B, chain_length, M)`` that receives tanh(theta) of every recorded sample (input of ``nk_forces_rbm``).
         ``stats_shift``: with an operator, also reduce the statistics' partial sums inside the launch (shifted by this
@@ -338,6 +339,8 @@ class MetropolisSampler:
             part = torch.empty(_lib.NK_STATS_NPARTIAL + 1, dtype=torch.float64, device=dev)
             part[_lib.NK_STATS_NPARTIAL] = float(B)
             a.stats_out, a.stats_shift = part.data_ptr(), float(stats_shift)
+            if no_handover:  # only the kernel NK_PATH_AUTO tries first; part[0] is NaN if it had to give up (caller repeats)
+                a.flags = _lib.NK_SWEEP_NO_HANDOVER
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().nk_sweep(_lib.stream_ptr(dev), C.byref(rbm), C.byref(chains), C.byref(a)))
         n_steps = (n_discard + chain_length) * self.sweep_size

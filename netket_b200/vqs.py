@@ -269,12 +269,19 @@ class MCState:
             hint = self._shift_hint
             shift = hint[1] if (hint is not None and hint[0] is operator) else 0.0
         out = sa._launch(self._model, self._variables, st, chain_length, n_discard=n_discard, operator=operator, path=path,
-                         tanh_out=self._tanh, stats_shift=shift)
+                         tanh_out=self._tanh, stats_shift=shift, no_handover=shift is not None and path == _lib.NK_PATH_AUTO)
+        stats = None
+        if shift is not None:
+            stats = self._finish_stats(out[2], out[4], shift, chain_length)
+            if stats is None:  # the optimistic single-kernel launch met weights outside its range: the full chain of kernels
+                out = sa._launch(self._model, self._variables, st, chain_length, n_discard=n_discard, operator=operator, path=path,
+                                 tanh_out=self._tanh, stats_shift=shift)
+                stats = self._finish_stats(out[2], out[4], shift, chain_length)
         samples, _, eloc, st = out[:4]
         self.sampler_state = st
         if shift is not None:
-            self._stats_cache = (operator, self._finish_stats(eloc, out[4], shift, chain_length))
-            self._shift_hint = (operator, self._stats_cache[1].mean)
+            self._stats_cache = (operator, stats)
+            self._shift_hint = (operator, stats.mean)
         return samples, eloc
 
     def _finish_stats(self, eloc, part, shift, L):
@@ -285,6 +292,8 @@ class MCState:
 
         _allreduce(part)
         p = part.tolist()
+        if p[0] != p[0]:
+            return None  # NK_SWEEP_NO_HANDOVER: the tuned kernel gave up on every rank (the weights are the same everywhere)
         n_chains_total = int(round(p[_lib.NK_STATS_NPARTIAL]))
         sums = p[:_lib.NK_STATS_NPARTIAL]
         ts = float(n_chains_total * L)

@@ -172,3 +172,40 @@ def test_statistics_flag_switches_to_the_fft_variant(cuda):
     # a constant chain has no autocorrelation function: tau is NaN, as jnp's 0 / 0
     c = torch.ones((4, 16), dtype=torch.float64, device="cuda")
     assert np.isnan(nk.stats.statistics_fft(c).tau_corr)
+
+
+@pytest.mark.parametrize("std", [0.5, 0.9])
+def test_optimistic_launch_repeats_with_the_full_chain_of_kernels_for_large_weights(cuda, std):
+    """NK_SWEEP_NO_HANDOVER: `expect` enqueues only the tuned fp32 kernel; weights beyond its range (std 0.5: max|W| ~ 2,
+    std 0.9: ~ 3.8) make it raise NaN in the partial sums, and MCState repeats the launch with the hand-over kernels."""
+    import netket_b200 as nk
+    from netket_b200 import _lib
+
+    vs, op = _state(nk, 10, 2, 4, np.float32, 128, 8, std=std)
+    st0 = vs.sampler_state
+    n0 = _lib.lib().nk_launch_count()
+    stats = vs.expect(op)
+    assert np.isfinite(stats.mean) and np.isfinite(stats.variance)
+    eloc = vs.local_estimators(op)
+    ref = oracle.stats.statistics(eloc.cpu().numpy().astype(np.float64))
+    np.testing.assert_allclose(stats.mean, ref["mean"], rtol=1e-10)
+    np.testing.assert_allclose(stats.variance, ref["variance"], rtol=1e-9)
+    # the same chains as a plain (non-optimistic) launch from the same state
+    sa = vs.sampler
+    s2, _, e2, _ = sa._launch(vs.model, vs.variables, st0.replace(n_steps_proc=0, n_accepted_proc=torch.zeros_like(st0.n_accepted_proc)),
+                              8, n_discard=3, operator=op)
+    assert torch.equal(s2, vs.samples) and torch.equal(e2, eloc)
+    assert _lib.lib().nk_launch_count() - n0 > 8  # two rounds of launches happened
+
+
+def test_expect_is_at_most_four_of_our_kernels_per_step(cuda):
+    """launches per `vs.reset(); vs.expect(H)` on the headline path: theta prep + theta GEMM + fused sweep."""
+    import netket_b200 as nk
+    from netket_b200 import _lib
+
+    vs, op = _state(nk, 10, 2, 4, np.float32, 256, 16, std=0.01)
+    vs.expect(op)
+    vs.reset()
+    n0 = _lib.lib().nk_launch_count()
+    vs.expect(op)
+    assert _lib.lib().nk_launch_count() - n0 <= 4
