@@ -243,7 +243,7 @@ int nk_sweep(void *stream, const nk_rbm_t *rbm, nk_chains_t *ch, const nk_sweep_
         guard = flags + 5;
       }
     } else {
-      rc = sweep_prod(st, k, theta, flags, tables);
+      rc = sweep_prod(st, k, theta, flags, tables, nullptr, 0, &stats_guard);
     }
     if (rc == NK_OK) {
       // weights beyond the product form's range (a property of the data, found by the prep kernels): the product kernel

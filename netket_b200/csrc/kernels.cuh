@@ -49,7 +49,9 @@ int sweep_fast(cudaStream_t stream, const SweepKernelArgs &a, const float *theta
 bool sweep_prod_supported(const SweepKernelArgs &a);
 size_t sweep_prod_workspace_bytes(const nk_rbm_t &rbm);
 // run_if: launch guard (NULL: always run); flags[giveup] is raised when the weights are outside the product form's range
+// stats_guard (out, optional): non-NULL afterwards iff the kernel launched first reduces the statistics of its energies itself
+// (SweepKernelArgs.stats_out); *stats_guard != 0 on the device then says that it handed over and K6 must run
 int sweep_prod(cudaStream_t stream, const SweepKernelArgs &a, const void *theta_ws, int *flags, void *tables_ws, const int *run_if = nullptr,
-               int giveup = 0);
+               int giveup = 0, const int **stats_guard = nullptr);
 
 }  // namespace nk

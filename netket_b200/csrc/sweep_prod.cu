@@ -355,14 +355,29 @@ bool sweep_prod_supported(const SweepKernelArgs &a) {
 }
 
 // bytes of workspace behind theta and the flags: the G table and the aux blob
-size_t sweep_prod_workspace_bytes(const nk_rbm_t &rbm) {
+size_t sweep_shadow_park_bytes();  // sweep_shadow.cu
+
+static size_t prod_tables_bytes(const nk_rbm_t &rbm) {
   ProdShape ps;
   if (rbm.N > 1024 || !prod_shape(rbm.M, rbm.dtype, NK_RULE_LOCAL, &ps)) return 0;
   return (((size_t)rbm.N * ps.kw * ps.seg_bytes + 255) & ~(size_t)255) + PROD_AUX_MAX;
 }
+size_t sweep_prod_workspace_bytes(const nk_rbm_t &rbm) {
+  const size_t t = prod_tables_bytes(rbm);
+  if (t == 0) return 0;
+  // fp64: room to park the double state of the chains in flight while they sweep on the fp32 shadow (sweep_shadow.cu)
+  return t + (rbm.dtype == NK_F64 ? sweep_shadow_park_bytes() : 0);
+}
+
+static size_t prod_tables_bytes(const nk_rbm_t &rbm);
+// sweep_shadow.cu
+bool sweep_shadow_supported(const SweepKernelArgs &a, const ProdLayout &L);
+int sweep_shadow(cudaStream_t stream, const ProdArgs &pa, int give, double *park);
+size_t sweep_shadow_park_bytes();
 
 int sweep_prod(cudaStream_t stream, const SweepKernelArgs &a, const void *theta_ws, int *flags, void *tables_ws, const int *run_if,
-               int giveup) {
+               int giveup, const int **stats_guard) {
+  if (stats_guard) *stats_guard = nullptr;
   ProdShape ps;
   ProdArgs pa{};
   if (!prod_shape(a.rbm.M, a.rbm.dtype, a.rule, &ps) || !prod_layout(a, ps, &pa.L)) {
@@ -391,6 +406,15 @@ int sweep_prod(cudaStream_t stream, const SweepKernelArgs &a, const void *theta_
   prod_prep_tables<double><<<1, 256, 0, stream>>>(pa, ps.ne_pad);
   NK_LAUNCH_OK();
   if (multi) return launch_prod_f64_local_multi(stream, pa, ps.nfull, ps.tail);
+  if (run_if == nullptr && sweep_shadow_supported(a, pa.L)) {
+    // fp32 shadow decisions + streamed double table (sweep_shadow.cu); if the weights are outside the shadow's range it raises
+    // flags[8] and the one-table kernel, queued behind with that guard, does the work
+    double *park = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(tables_ws) + prod_tables_bytes(a.rbm));
+    int rc = sweep_shadow(stream, pa, 8, park);
+    if (rc) return rc;
+    pa.run_if = flags + 8;
+    if (stats_guard) *stats_guard = flags + 8;  // the shadow kernel reduces its energies itself
+  }
   return a.rule == NK_RULE_LOCAL ? launch_prod_f64_local(stream, pa, ps.nfull, ps.tail)
                                  : launch_prod_f64_exchange(stream, pa, ps.nfull, ps.tail);
 }
