@@ -20,14 +20,14 @@ static int dtype_code(ffi::DataType t) { return t == ffi::DataType::F32 ? NK_F32
 
 static ffi::Error fail() { return ffi::Error(ffi::ErrorCode::kInternal, nk_last_error()); }
 
-// samples, log_prob, sigma', n_accepted', E_loc  =  sweep(W, b, a, sigma, n_accepted, edges; attrs)
+// samples, log_prob, sigma', n_accepted', E_loc, statistics sums  =  sweep(W, b, a, sigma, n_accepted, edges; attrs)
 static ffi::Error SweepImpl(cudaStream_t stream, ffi::AnyBuffer W, ffi::AnyBuffer b, ffi::AnyBuffer a, ffi::Buffer<ffi::S8> sigma,
                             ffi::Buffer<ffi::S64> n_accepted, ffi::Buffer<ffi::S32> edges, ffi::Result<ffi::Buffer<ffi::S8>> samples,
                             ffi::Result<ffi::AnyBuffer> log_prob, ffi::Result<ffi::Buffer<ffi::S8>> sigma_out,
                             ffi::Result<ffi::Buffer<ffi::S64>> n_accepted_out, ffi::Result<ffi::AnyBuffer> eloc,
-                            ffi::Result<ffi::Buffer<ffi::U8>> workspace, int32_t rule, int32_t chain_length, int32_t n_discard,
-                            int32_t sweep_size, double machine_pow, double h, double J, uint64_t seed, uint64_t t,
-                            uint64_t chain_offset) {
+                            ffi::Result<ffi::Buffer<ffi::F64>> sums, ffi::Result<ffi::Buffer<ffi::U8>> workspace, int32_t rule,
+                            int32_t chain_length, int32_t n_discard, int32_t sweep_size, double machine_pow, double h, double J,
+                            double stats_shift, uint64_t seed, uint64_t t, uint64_t chain_offset) {
   const auto dims = sigma.dimensions();
   const int64_t B = dims[0];
   const int32_t N = (int32_t)dims[1];
@@ -49,6 +49,8 @@ static ffi::Error SweepImpl(cudaStream_t stream, ffi::AnyBuffer W, ffi::AnyBuffe
   args.eloc_out = eloc->untyped_data();
   args.eloc_dtype = dtype_code(eloc->element_type());
   args.path = NK_PATH_AUTO;
+  args.stats_out = sums->typed_data();  // NK_STATS_NPARTIAL doubles: psum over the mesh, then nk_stats_finalize's arithmetic
+  args.stats_shift = stats_shift;
   return nk_sweep(stream, &rbm, &ch, &args) == NK_OK ? ffi::Error::Success() : fail();
 }
 
@@ -66,6 +68,7 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(NkSweep, SweepImpl,
                                   .Ret<ffi::Buffer<ffi::S8>>()    // sigma'
                                   .Ret<ffi::Buffer<ffi::S64>>()   // n_accepted'
                                   .Ret<ffi::AnyBuffer>()          // E_loc (B, chain_length)
+                                  .Ret<ffi::Buffer<ffi::F64>>()   // shifted statistics sums (NK_STATS_NPARTIAL)
                                   .Ret<ffi::Buffer<ffi::U8>>()    // workspace (nk_sweep_workspace_bytes)
                                   .Attr<int32_t>("rule")
                                   .Attr<int32_t>("chain_length")
@@ -74,6 +77,7 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(NkSweep, SweepImpl,
                                   .Attr<double>("machine_pow")
                                   .Attr<double>("h")
                                   .Attr<double>("J")
+                                  .Attr<double>("stats_shift")
                                   .Attr<uint64_t>("seed")
                                   .Attr<uint64_t>("t")
                                   .Attr<uint64_t>("chain_offset"));

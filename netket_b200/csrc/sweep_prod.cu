@@ -204,7 +204,7 @@ struct ProdShape {
 };
 
 // shape of one warp's segment holding `m` hidden units
-static bool seg_shape(int m, int dtype, ProdShape *ps) {
+static bool seg_shape(int m, int dtype, ProdShape *ps, int max_full_f32 = 4) {
   const int esz = dtype == NK_F32 ? 4 : 8;
   const int chunk = 512 / esz;  // elements per 512-byte chunk
   int nfull = m / chunk, rem = m % chunk, tail = 0;
@@ -218,7 +218,7 @@ static bool seg_shape(int m, int dtype, ProdShape *ps) {
     nfull += 1;
     tail = 0;
   }
-  const int max_full = esz == 4 ? 4 : 8;
+  const int max_full = esz == 4 ? max_full_f32 : 8;
   if (m < 1 || nfull > max_full || (nfull == max_full && tail != 0)) return false;
   ps->nfull = nfull;
   ps->tail = tail;
@@ -236,6 +236,9 @@ static int prod_warps(int dtype, int rule) {
 
 // M <= 512: one warp per chain.  Larger hidden layers (LocalRule): kw warps per chain, chosen to waste the least padding
 // among the instantiated segment shapes (at least half-full segments), then the fewest warps.
+#ifndef NK_PROD_MULTI_MAX_FULL_F32
+#define NK_PROD_MULTI_MAX_FULL_F32 5
+#endif
 static bool prod_shape(int M, int dtype, int rule, ProdShape *ps) {
   if (seg_shape(M, dtype, ps)) {
     ps->kw = 1;
@@ -249,7 +252,10 @@ static bool prod_shape(int M, int dtype, int rule, ProdShape *ps) {
   for (int kw = 2; kw <= 16 && kw <= warps; ++kw) {
     ProdShape c;
     const int mw = (M + kw - 1) / kw;
-    if (!seg_shape(mw, dtype, &c) || c.nfull < min_full) continue;
+    // fp32 segments of up to 5 x 128 units (20 per lane) exist for the multi-warp kernel only: fewer, fatter warps per chain
+    // mean more chains in flight per SM (M = 3200: 5 warps x 640 units, 4 chains per SM instead of 2)
+    if (!seg_shape(mw, dtype, &c, NK_PROD_MULTI_MAX_FULL_F32) || c.nfull < min_full) continue;
+    if (c.nfull == 5 && c.tail != 0) continue;
     const long cost = (long)kw * c.mp * 64 + kw;
     if (best < 0 || cost < best) {
       best = cost;

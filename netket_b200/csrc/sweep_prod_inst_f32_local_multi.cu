@@ -13,6 +13,7 @@ int launch_prod_f32_local_multi(cudaStream_t stream, const ProdArgs &a, int nful
   NK_PROD_CASE(3, 1)
   NK_PROD_CASE(3, 2)
   NK_PROD_CASE(4, 0)
+  NK_PROD_CASE(5, 0)
 #undef NK_PROD_CASE
   set_error("sweep_prod: no instantiation for this number of hidden units");
   return NK_EUNSUPPORTED;

@@ -33,11 +33,12 @@ namespace shadow {
 
 using namespace fast;
 
-constexpr int WARPS = 16;
+constexpr int WARPS = 12;
 constexpr int THREADS = WARPS * 32;
 constexpr int STAGES = 12;       // rows of the double table in flight
 constexpr int LAG = 4;           // the producer refills the stage of the row consumed LAG rows ago
-constexpr int BAND = 192;        // fixed-point units (2^-19 in log2): decisions closer than this to the threshold are re-decided in fp64
+constexpr int BAND = 64;         // fixed-point units (2^-19 in log2): decisions closer than this to the threshold are re-decided in fp64
+                                 // (the shadow's error: ~2 units typical; PROD_FX_BAND of the one-table kernel is the same 64)
 constexpr float SH_EXP_RANGE = 100.0f;
 constexpr int SIG_STRIDE = 128;  // spin bytes per warp
 constexpr int WSTAT = 12;
@@ -97,29 +98,57 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// fp64 re-decision of one proposal from scratch (rare): theta_j = b_j + sum_i sigma_i W_ij, delta = 2 nu a_i +
-// sum_j [lncosh(theta_j + 2 nu W_ij) - lncosh(theta_j)], accept <=> u < exp(machine_pow * delta)   (metropolis.py:441-450)
-static __device__ __noinline__ bool exact_accept(const nk_rbm_t &rbm, uint32_t sig_s, int site, bool sdown, double u, double pw, int lane) {
-  const int N = rbm.N, M = rbm.M;
-  const double *W = reinterpret_cast<const double *>(rbm.W);
-  const double *b = reinterpret_cast<const double *>(rbm.b);
-  const double *a = reinterpret_cast<const double *>(rbm.a);
-  const double nu2 = sdown ? 2.0 : -2.0;  // 2 nu, nu = -sigma_site
-  double acc = 0.0;
-  for (int j0 = 0; j0 < M; j0 += 32) {
-    const int j = j0 + lane;
-    if (j < M) {
-      double th = b != nullptr ? b[j] : 0.0;
-      for (int i = 0; i < N; ++i) {
-        const double w = W[(size_t)i * M + j];
-        th += lds_u8(sig_s + i) ? -w : w;
+// fp64 re-decision of one proposal (rare, ~3e-4 of the proposals).  The double state as of the last update is parked in the
+// workspace; the sites flipped since then are the bytes where sigma differs from its copy of that moment.  The state is
+// brought up to date in registers (one double row per such site, straight from the L2-resident table), the proposal's product
+// is formed in double and  accept <=> u < exp(machine_pow * (x_i +- y_i + sum_lanes log(P / norm)))   (metropolis.py:441-450).
+template <int NF64, int TL>
+static __device__ __noinline__ bool exact_accept(const ProdArgs &p, const double *park, uint32_t sig_s, uint32_t sigp_s, int site, bool sdown,
+                                                 double u, double pw, int lane) {
+  using LD = prod::LaneMap<double, NF64, TL>;
+  constexpr int NV = LD::NV;
+  constexpr uint32_t FULL = 0xffffffffu;
+  const int N = p.s.rbm.N;
+  double A[NV], Bv[NV];
+#pragma unroll
+  for (int e = 0; e < NV; ++e) {
+    A[e] = park[(size_t)(2 * e) * 32];
+    Bv[e] = park[(size_t)(2 * e + 1) * 32];
+  }
+  auto load_row = [&](int i, double(&g)[NV]) {
+    const unsigned char *row = p.gtab + (size_t)i * p.L.row_bytes;
+    prod::load_row_p<NF64, TL>(row + 16 * lane, row + LD::TAIL_OFF + LD::TAIL_LANE * lane, g);
+  };
+  for (int b = 0; b < 4; ++b) {
+    const int idx = 32 * b + lane;
+    const uint32_t now = idx < N ? lds_u8(sig_s + idx) : 0u, was = idx < N ? lds_u8(sigp_s + idx) : 0u;
+    uint32_t fl = __ballot_sync(FULL, now != was);
+    const uint32_t dn = __ballot_sync(FULL, now != 0u);
+    while (fl != 0u) {
+      const int bit = __ffs(fl) - 1;
+      fl &= fl - 1u;
+      double g[NV];
+      load_row(32 * b + bit, g);
+      if ((dn >> bit) & 1u) {  // +1 -> -1: A <- A G
+#pragma unroll
+        for (int e = 0; e < NV; ++e) A[e] *= g[e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < NV; ++e) Bv[e] *= g[e];
       }
-      acc += lncosh_diff(th + nu2 * W[(size_t)site * M + j], th);
     }
   }
-  acc = warp_sum(acc);
-  if (a != nullptr) acc += nu2 * a[site];
-  return u < exp(pw * acc);
+  double g[NV];
+  load_row(site, g);
+  double P = 1.0, nrm = 1.0;
+#pragma unroll
+  for (int e = 0; e < NV; ++e) {
+    P *= sdown ? fma(Bv[e], g[e], A[e]) : fma(A[e], g[e], Bv[e]);
+    nrm *= A[e] + Bv[e];
+  }
+  const double d = warp_sum(log(P / nrm));
+  const RcD &rc = reinterpret_cast<const RcD *>(p.aux + p.L.rc_off)[site];
+  return u < exp(pw * ((sdown ? rc.xn + rc.yn : rc.xn - rc.yn) + d));
 }
 
 template <int NF32, int TL>
@@ -223,6 +252,9 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_shadow_kernel(const __grid_c
   const int n_rounds = (int)((s.B + per_round - 1) / per_round);
   const uint32_t passes_per_round = (uint32_t)n_sweeps + (want_eloc ? (uint32_t)CL : 0u);
   const uint32_t total_q = (uint32_t)n_rounds * passes_per_round * (uint32_t)N;
+  // every CTA walks the table from its own starting row: 148 CTAs asking L2 for the same row at the same moment serialise
+  // on its slices (measured: 830 cycles per row in lockstep)
+  const uint32_t rot = (uint32_t)(((unsigned long long)blockIdx.x * (unsigned)N) / gridDim.x) % (uint32_t)N;
   uint32_t q = 0;           // rows consumed by this warp so far
   uint32_t next_issue = 0;  // producer only (warp 0, lane 0): rows issued so far
   auto produce = [&](uint32_t upto) {  // warp 0: keep the ring filled up to row `upto` (exclusive) of the stream
@@ -231,7 +263,7 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_shadow_kernel(const __grid_c
       if (next_issue >= (uint32_t)STAGES) mbar_wait_uniform(empty + st, ((next_issue / STAGES) - 1u) & 1u);
       if (lane == 0) {
         mbar_expect_tx(full + st, (uint32_t)row64);
-        tma_bulk_g2s(smem + L.ring + (size_t)st * row64, p.gtab + (size_t)(next_issue % (uint32_t)N) * row64, (uint32_t)row64, full + st);
+        tma_bulk_g2s(smem + L.ring + (size_t)st * row64, p.gtab + (size_t)((next_issue + rot) % (uint32_t)N) * row64, (uint32_t)row64, full + st);
       }
       ++next_issue;
     }
@@ -390,7 +422,8 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_shadow_kernel(const __grid_c
         if (idx < N) sts_u8(sigp_s + idx, now);
       }
       // U: the double state follows the net change of the sweep
-      for (int i = 0; i < N; ++i) {
+      for (int ii = 0; ii < N; ++ii) {
+        const int i = (ii + (int)rot) % N;  // the row in this stage
         const uint32_t rs = row_wait();
         if ((sw4sel4(fl, i >> 5) >> (i & 31)) & 1u) {
           double g[NV];
@@ -449,8 +482,8 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_shadow_kernel(const __grid_c
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
               v[jj] = 1.0;
-              const int i = base + jj;
-              if (i < N) {
+              const int i = (base + jj + (int)rot) % N;
+              if (base + jj < N) {
                 const uint32_t rs = row_wait();
                 double g[NV];
                 prod::load_row_s<NF64, TL>(rs + 16u * lane_o, rs + (uint32_t)LD::TAIL_OFF + (uint32_t)LD::TAIL_LANE * lane_o, g);
@@ -461,8 +494,8 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_shadow_kernel(const __grid_c
               }
             }
             const double tot = prod::bfly<double, 8>(v, lane_o);
-            const int mys = base + myidx;
-            if ((lane_o & 1) == 0 && lane_o < 16 && mys < N) {
+            const int mys = (base + myidx + (int)rot) % N;
+            if ((lane_o & 1) == 0 && lane_o < 16 && base + myidx < N) {
               const double2 cst = rcd[mys];
               off_l += tot * (((sw4sel4(dn, mys >> 5) >> (mys & 31)) & 1u) ? cst.x : cst.y) / nrm;
             }
@@ -530,9 +563,12 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_shadow_kernel(const __grid_c
       }
       const int nb = min(32, T_total - tt);
       int k = 0;
+      // forced: 0 none, 1 / 2 = the proposal at k was re-decided in double precision (reject / accept)
+      int forced = 0;
       while (k < nb) {
         const int kend = k + min(nb - k, sweep_size - in_sweep);
-        in_sweep += kend - k;
+        const int k0 = k;
+        bool need_exact = false;
         for (; k < kend; ++k) {
           const uint4 rec = lds128u(rec_s + 16u * k);
           const uint32_t sdown = lds_u8(rec.y);
@@ -548,15 +584,15 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_shadow_kernel(const __grid_c
           const int margin = (int)((uint32_t)Rp - (uint32_t)c.R + (sdown ? rec.w : 0u - rec.w) - rec.z);  // > 0 <=> accept
           bool acc = margin > 0;
           if (margin <= BAND && margin >= -BAND) {
-            // inside the shadow's error band: the decision of the double-precision chain, from scratch
-            const int site = (int)(rec.y - sig_s);
-            double u;
-            if (s.stream_w0 != nullptr)
-              u = reinterpret_cast<const double *>(s.stream_u)[(size_t)(tt + k) * s.B + chain];
-            else
-              u = uniform_from_words<double>(philox_words(s.seed, s.t0 + (uint64_t)(tt + k), gchain, STREAM_STEP));
-            acc = pw > 0.0 ? __any_sync(FULL, exact_accept(s.rbm, sig_s, site, sdown != 0u, u, pw, lane_o)) != 0 : true;
+            // inside the shadow's error band: leave the loop, decide in double precision (a function call: kept out of the
+            // hot loop, whose registers it would otherwise push to the stack), come back to this proposal with the verdict
+            if (forced == 0) {
+              need_exact = true;
+              break;
+            }
+            acc = forced == 2;
           }
+          forced = 0;
           if (acc) {
             if (sdown) {
 #pragma unroll
@@ -571,6 +607,20 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_shadow_kernel(const __grid_c
             sts_u8(rec.y, sdown ^ 1u);
             if (++c.nacc == c.next_renorm) renormalise32();
           }
+        }
+        in_sweep += k - k0;
+        if (need_exact) {
+          const uint4 rec = lds128u(rec_s + 16u * k);
+          const uint32_t sdown = lds_u8(rec.y);
+          const int site = (int)(rec.y - sig_s);
+          double u;
+          if (s.stream_w0 != nullptr)
+            u = reinterpret_cast<const double *>(s.stream_u)[(size_t)(tt + k) * s.B + chain];
+          else
+            u = uniform_from_words<double>(philox_words(s.seed, s.t0 + (uint64_t)(tt + k), gchain, STREAM_STEP));
+          const bool ok = pw > 0.0 ? __any_sync(FULL, exact_accept<NF64, TL>(p, park, sig_s, sigp_s, site, sdown != 0u, u, pw, lane_o)) != 0 : true;
+          forced = ok ? 2 : 1;
+          continue;
         }
         if (in_sweep == sweep_size) {
           in_sweep = 0;

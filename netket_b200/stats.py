@@ -425,3 +425,116 @@ def acf_window_saturated(estimator):
 def tau_corr_reliable(estimator):
     """check_mc_convergence.py:258-272: window not saturated and at least 50 effective samples per chain."""
     return bool(estimator._summarise()["out"][8])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# K-channel streaming statistics with a combinator (netket/_src/stats/online_stats/accumulator_batch.py:71-257)
+# ------------------------------------------------------------------------------------------------------------------
+class StatsBatch:
+    """Statistics of an array-valued estimator (netket/stats/mc_stats.py:183-207): ``mean`` and ``error_of_mean`` have the
+    shape of the combinator's output; scalar diagnostics are not defined."""
+
+    __slots__ = ("mean", "error_of_mean")
+
+    def __init__(self, mean, error_of_mean):
+        self.mean, self.error_of_mean = mean, error_of_mean
+
+    @property
+    def shape(self):
+        return tuple(self.mean.shape)
+
+    def __repr__(self):
+        return f"StatsBatch(shape={self.shape}, max_err={float(self.error_of_mean.abs().max()):.4g})"
+
+
+def _delta_method_stats(f, X, Cov):
+    """accumulator_batch.py:31-68: Var[f_i(X)] ~ J_i^T Cov J_i with J = d f / d X (forward-mode Jacobian of the torch
+    combinator); a scalar combinator gives a ``Stats``, an array-valued one a ``StatsBatch``; ``Cov = None`` -> NaN errors."""
+    mean = f(X)
+    scalar = mean.ndim == 0
+    if Cov is None:
+        if scalar:
+            return Stats(mean=float(mean), error_of_mean=math.nan)
+        return StatsBatch(mean, torch.full_like(mean, math.nan))
+    J = torch.func.jacfwd(f)(X)  # (*out_shape, K)
+    err = torch.sqrt(torch.clamp(torch.einsum("...k,kl,...l->...", J, Cov, J), min=0.0))
+    if scalar:
+        return Stats(mean=float(mean), error_of_mean=float(err))
+    return StatsBatch(mean, err)
+
+
+class OnlineStatsBatch:
+    """K ``OnlineStats`` accumulators (one per channel of an ``(n_chains, chain_length, K)`` estimator, each updated by the
+    streaming kernel) and a combinator ``f: (K,) -> scalar | array`` of their means; errors by the delta method on the
+    covariance of the chain means (accumulator_batch.py:71-225).  ``combinator`` is a function of a float64 torch vector
+    (differentiated with ``torch.func.jacfwd``, the stand-in for ``jax.jacfwd``)."""
+
+    def __init__(self, estimators, combinator):
+        self.estimators = tuple(estimators)
+        self.combinator = combinator
+
+    @classmethod
+    def from_data(cls, data, combinator, *, max_lag=64):
+        data = data if isinstance(data, torch.Tensor) else torch.as_tensor(np.asarray(data))
+        if data.ndim != 3:
+            raise ValueError(f"data must be 3D, got {data.ndim}D")
+        from .utils import default_device
+
+        dev = data.device if data.is_cuda else default_device()
+        ests = tuple(OnlineStats(data.shape[0], max_lag=max_lag, device=dev) for _ in range(data.shape[-1]))
+        return cls(ests, combinator).update(data)
+
+    def update(self, data):
+        data = data if isinstance(data, torch.Tensor) else torch.as_tensor(np.asarray(data))
+        if data.ndim != 3 or data.shape[-1] != len(self.estimators):
+            raise ValueError(f"data must have shape (n_chains, chain_length, {len(self.estimators)})")
+        dev = self.estimators[0]._chain_count.device
+        data = data.to(dev)
+        return OnlineStatsBatch(tuple(e.update(data[..., k].contiguous()) for k, e in enumerate(self.estimators)), self.combinator)
+
+    @property
+    def n_samples(self):
+        return self.estimators[0].n_samples
+
+    @property
+    def n_chains(self):
+        """Chains of all ranks."""
+        t = torch.tensor([float(self.estimators[0].n_chains)], dtype=torch.float64, device=self.estimators[0]._chain_count.device)
+        return int(round(float(_allreduce(t).item())))
+
+    def _means(self):
+        dev = self.estimators[0]._chain_count.device
+        return torch.tensor([e.get_stats().mean for e in self.estimators], dtype=torch.float64, device=dev)
+
+    @property
+    def mean(self):
+        return self.combinator(self._means())
+
+    @property
+    def error_of_mean(self):
+        return self.get_stats().error_of_mean
+
+    def get_stats(self):
+        X = self._means()
+        n_chains = self.n_chains
+        if n_chains < 2 or bool(torch.isnan(X).any()):
+            return _delta_method_stats(self.combinator, X, None)
+        dev = torch.stack([e.chain_means for e in self.estimators]) - X[:, None]  # this rank's chains
+        Cov = _allreduce(dev @ dev.T) / n_chains ** 2                             # sum over the chains of all ranks
+        return _delta_method_stats(self.combinator, X, Cov)
+
+    def to_dict(self):
+        return self.get_stats().to_dict()
+
+    def to_compound(self):
+        return self.get_stats().to_compound()
+
+    def __repr__(self):
+        return repr(self.get_stats())
+
+
+def online_statistics_batch(data, combinator, old_estimator=None, *, max_lag=64):
+    """accumulator_batch.py:228-248."""
+    if old_estimator is None:
+        return OnlineStatsBatch.from_data(data, combinator, max_lag=max_lag)
+    return old_estimator.update(data)

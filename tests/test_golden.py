@@ -188,4 +188,4 @@ def test_cuda_statistics_golden(cuda, tag):
 
     st = nk.stats.statistics(_cuda(G[f"{tag}_data"]))
     got = np.array([st.mean, st.error_of_mean, st.variance, st.tau_corr, st.R_hat])
-    np.testing.assert_allclose(got, G[f"{tag}_result"], rtol=1e-10, equal_nan=True)
+    np.testing.assert_allclose(got, G[f"{tag}_result"], rtol=1e-10, atol=1e-14, equal_nan=True)

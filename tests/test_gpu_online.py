@@ -281,3 +281,39 @@ def test_thermalise(cuda):
     one, H1 = small_state(nk, n_chains=1, n_samples=4)
     with pytest.raises(ValueError, match="at least 2 chains"):
         one.thermalise(H1, verbose=False)
+
+
+def test_online_stats_batch_delta_method(cuda):
+    """OnlineStatsBatch (accumulator_batch.py:71-225): K channels accumulated by the streaming kernel, a scalar and an
+    array-valued combinator, errors by the delta method on the covariance of the chain means - against the same formulas in
+    NumPy (Cov = D D^T / n_chains^2, Var f = J Cov J^T) with the analytic Jacobians."""
+    import netket_b200 as nk
+
+    rs = np.random.default_rng(11)
+    n_chains, K = 24, 3
+    batches = [rs.normal(size=(n_chains, L, K)) * [1.0, 0.5, 2.0] + [1.0, -2.0, 0.5] for L in (7, 16, 5)]
+    f = lambda X: X[2] - X[0] * X[1]  # noqa: E731  (a connected correlator)
+    acc = None
+    for b in batches:
+        acc = nk.stats.online_statistics_batch(torch.from_numpy(b).cuda(), f, acc, max_lag=8)
+    allx = np.concatenate(batches, axis=1)
+    X = allx.mean(axis=(0, 1))
+    cm = allx.mean(axis=1)  # chain means (n_chains, K)
+    D = (cm - X).T
+    Cov = D @ D.T / n_chains ** 2
+    J = np.array([-X[1], -X[0], 1.0])
+    st = acc.get_stats()
+    np.testing.assert_allclose(st.mean, X[2] - X[0] * X[1], rtol=1e-12)
+    np.testing.assert_allclose(st.error_of_mean, np.sqrt(J @ Cov @ J), rtol=1e-10)
+    assert acc.n_samples == n_chains * 28 and acc.n_chains == n_chains
+    g = lambda X: torch.stack([X[0] + X[1], X[0] * X[2]])  # noqa: E731
+    accg = nk.stats.OnlineStatsBatch.from_data(torch.from_numpy(allx).cuda(), g, max_lag=8)
+    sb = accg.get_stats()
+    Jg = np.array([[1.0, 1.0, 0.0], [X[2], 0.0, X[0]]])
+    assert sb.shape == (2,)
+    np.testing.assert_allclose(sb.mean.cpu().numpy(), [X[0] + X[1], X[0] * X[2]], rtol=1e-12)
+    np.testing.assert_allclose(sb.error_of_mean.cpu().numpy(), np.sqrt(np.einsum("ik,kl,il->i", Jg, Cov, Jg)), rtol=1e-10)
+    one = nk.stats.OnlineStatsBatch.from_data(torch.from_numpy(allx[:1]).cuda(), f, max_lag=4)
+    assert np.isnan(one.get_stats().error_of_mean)  # fewer than two chains: no covariance (accumulator_batch.py:199-200)
+    with pytest.raises(ValueError, match="3D"):
+        nk.stats.OnlineStatsBatch.from_data(torch.zeros((4, 4)).cuda(), f)
