@@ -11,7 +11,7 @@
 //      fp64 chain, bit for bit, and no double is touched while sweeping.
 //   U  update, once per sweep.  The double state only has to follow the NET change of the sweep: a site flipped an even number
 //      of times multiplies A_j and B_j by the same G_ij, which cancels in every ratio.  The double table is streamed once
-//      through a shared-memory ring by TMA bulk copies (one producer thread, full / empty mbarriers) and every warp applies the
+//      through a shared-memory ring by TMA bulk copies of 4 rows (one producer thread, full / empty mbarriers) and every warp applies the
 //      rows of its chain's net-flipped sites (~43 of 100) to its (A, B) registers; the state is rescaled by exact powers
 //      of two and the shadow is refreshed from it (its rounding drift never outlives a sweep).
 //   E  local energy of a recorded sample: the table is streamed a second time, every warp forms prod_j (X_j G_ij + Y_j) for
@@ -33,10 +33,18 @@ namespace shadow {
 
 using namespace fast;
 
-constexpr int WARPS = 12;
+constexpr int WARPS = 12;         // warp 0 only feeds the ring of double rows (TMA); warps 1 .. 11 own one chain each
+constexpr int CWARPS = WARPS - 1;  // consumer warps = chains in flight per CTA
 constexpr int THREADS = WARPS * 32;
-constexpr int STAGES = 12;       // rows of the double table in flight
-constexpr int LAG = 4;           // the producer refills the stage of the row consumed LAG rows ago
+#ifndef NK_SH_GROUP
+#define NK_SH_GROUP 4
+#endif
+#ifndef NK_SH_STAGES
+#define NK_SH_STAGES 3
+#endif
+constexpr int GROUP = NK_SH_GROUP;  // rows per TMA bulk copy (one 3.3 KB row per copy ran at ~1 row / 1000 cycles: the copy engine
+                                 // wants fewer, larger requests)
+constexpr int STAGES = NK_SH_STAGES;  // groups of rows in the ring: one being read, the others in flight
 constexpr int BAND = 64;         // fixed-point units (2^-19 in log2): decisions closer than this to the threshold are re-decided in fp64
                                  // (the shadow's error: ~2 units typical; PROD_FX_BAND of the one-table kernel is the same 64)
 constexpr float SH_EXP_RANGE = 100.0f;
@@ -66,7 +74,7 @@ __host__ __device__ inline Layout make_layout(int N, int MP32, int row64, int E)
   L.wstat = o;
   o += WARPS * WSTAT * 8;
   L.ring = o;
-  o += STAGES * row64;
+  o += STAGES * GROUP * row64;
   L.bars = o;
   o += (2 * STAGES + 2) * 8;
   L.red = o;
@@ -86,8 +94,8 @@ __device__ __forceinline__ void mbar_wait_uniform(uint64_t *bar, uint32_t parity
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"  // non-blocking probe: try_wait suspends the thread for a
+        "selp.u32 %0, 1, 0, p;\n"                                     // system-chosen time (measured: ~0.5 us per ring hand-over)
         "}\n"
         : "=r"(done)
         : "r"(smem_u32(bar)), "r"(parity)
@@ -96,6 +104,21 @@ __device__ __forceinline__ void mbar_wait_uniform(uint64_t *bar, uint32_t parity
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// prod_e (X_e g_e + Y_e) with four interleaved accumulators (dependency depth ~ NV / 4 + 2 instead of NV / 2 + 1)
+template <int NV>
+__device__ __forceinline__ double lane_product64(const double (&X)[NV], const double (&Y)[NV], const double (&g)[NV]) {
+  double acc[4] = {1.0, 1.0, 1.0, 1.0};
+#pragma unroll
+  for (int e = 0; e < NV; ++e) {
+    const double c = fma(X[e], g[e], Y[e]);
+    acc[e & 3] = e < 4 ? c : acc[e & 3] * c;
+  }
+  if (NV == 1) return acc[0];
+  if (NV == 2) return acc[0] * acc[1];
+  if (NV == 3) return (acc[0] * acc[1]) * acc[2];
+  return (acc[0] * acc[1]) * (acc[2] * acc[3]);
 }
 
 // fp64 re-decision of one proposal (rare, ~3e-4 of the proposals).  The double state as of the last update is parked in the
@@ -219,8 +242,8 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_shadow_kernel(const __grid_c
   for (int e = lane; e < WSTAT; e += 32) wstat[warp * WSTAT + e] = 0.0;
   if (tid == 0) {
     for (int st = 0; st < STAGES; ++st) {
-      mbar_init(full + st, 1);
-      mbar_init(empty + st, WARPS);
+      mbar_init(full + st, 1);        // the producer's expect_tx; completed by the bytes of the bulk copy
+      mbar_init(empty + st, CWARPS);  // one arrival per consumer warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -248,48 +271,61 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_shadow_kernel(const __grid_c
   double *ws = wstat + warp * WSTAT;
 
   // ---------------- the stream of double rows: every pass (U of every sweep, E of every recorded sweep) is rows 0 .. N-1
-  const int per_round = gridDim.x * WARPS;
+  const int per_round = gridDim.x * CWARPS;
   const int n_rounds = (int)((s.B + per_round - 1) / per_round);
   const uint32_t passes_per_round = (uint32_t)n_sweeps + (want_eloc ? (uint32_t)CL : 0u);
-  const uint32_t total_q = (uint32_t)n_rounds * passes_per_round * (uint32_t)N;
-  // every CTA walks the table from its own starting row: 148 CTAs asking L2 for the same row at the same moment serialise
-  // on its slices (measured: 830 cycles per row in lockstep)
-  const uint32_t rot = (uint32_t)(((unsigned long long)blockIdx.x * (unsigned)N) / gridDim.x) % (uint32_t)N;
-  uint32_t q = 0;           // rows consumed by this warp so far
-  uint32_t next_issue = 0;  // producer only (warp 0, lane 0): rows issued so far
-  auto produce = [&](uint32_t upto) {  // warp 0: keep the ring filled up to row `upto` (exclusive) of the stream
-    while (next_issue < upto && next_issue < total_q) {  // uniform over the warp; lane 0 issues
-      const uint32_t st = next_issue % STAGES;
-      if (next_issue >= (uint32_t)STAGES) mbar_wait_uniform(empty + st, ((next_issue / STAGES) - 1u) & 1u);
+  const int NG = (N + GROUP - 1) / GROUP;  // groups of rows per pass
+  const uint32_t total_q = (uint32_t)n_rounds * passes_per_round * (uint32_t)NG;
+  // every CTA walks the table from its own starting group: 148 CTAs asking L2 for the same rows at the same moment
+  // serialise on its slices
+  const int rotg = (int)((((unsigned long long)blockIdx.x * (unsigned)NG) / gridDim.x) % (unsigned)NG);
+  const uint32_t stage_bytes = (uint32_t)(GROUP * row64);
+  if (warp == 0) {
+    // ---------------- producer: one TMA bulk copy per group, as soon as every consumer warp has released the stage.
+    // (When the consumers also issued the copies - by TMA from warp 0 or by cp.async from all warps, both were built - every
+    // group hand-over cost ~0.5 us of bookkeeping and exposed L2 latency in all warps at once.)
+    int gi = rotg;
+    uint32_t st = 0, par = 0;  // parity of the `empty` phase to wait for (the stage's previous use); first waited at t = STAGES
+    for (uint32_t t = 0; t < total_q; ++t) {
+      if (t >= (uint32_t)STAGES) mbar_wait_uniform(empty + st, par);
       if (lane == 0) {
-        mbar_expect_tx(full + st, (uint32_t)row64);
-        tma_bulk_g2s(smem + L.ring + (size_t)st * row64, p.gtab + (size_t)((next_issue + rot) % (uint32_t)N) * row64, (uint32_t)row64, full + st);
+        const uint32_t bytes = (uint32_t)(min(GROUP, N - GROUP * gi) * row64);
+        mbar_expect_tx(full + st, bytes);
+        tma_bulk_g2s(smem + L.ring + (size_t)st * stage_bytes, p.gtab + (size_t)(GROUP * gi) * row64, bytes, full + st);
       }
-      ++next_issue;
+      __syncwarp();
+      if (++gi == NG) gi = 0;
+      if (++st == (uint32_t)STAGES) {
+        st = 0;
+        if (t + 1 > (uint32_t)STAGES) par ^= 1u;  // uses 1, 2, 3, ... of a stage wait for phases 0, 1, 0, ...
+      }
+    }
+  }
+  // consumer side of the ring: stage, parity and table group of the next group in the stream, kept incrementally
+  uint32_t cst = 0, cpar = 0;
+  int cgi = rotg;
+  auto grp_wait = [&]() -> uint32_t {  // wait for the next group of the stream; returns the shared address of its first row
+    mbar_wait_uniform(full + cst, cpar);
+    return ring_s + cst * stage_bytes;
+  };
+  auto grp_done = [&]() {  // this warp has read the group's rows into registers (or skipped them)
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + cst);
+    if (++cgi == NG) cgi = 0;
+    if (++cst == (uint32_t)STAGES) {
+      cst = 0;
+      cpar ^= 1u;
     }
   };
-  // wait for the next row of the stream; returns its shared address (lane part added by the caller)
-  auto row_wait = [&]() -> uint32_t {
-    const uint32_t st = q % STAGES;
-    mbar_wait_uniform(full + st, (q / STAGES) & 1u);
-    return ring_s + st * (uint32_t)row64;
-  };
-  auto row_done = [&]() {  // this warp has read the row into registers (or skipped it)
-    __syncwarp();
-    if (lane == 0) mbar_arrive(empty + (q % STAGES));
-    ++q;
-    if (warp == 0) produce(q + (uint32_t)(STAGES - LAG));
-  };
-  if (warp == 0) produce((uint32_t)(STAGES - LAG));
 
-  for (int round = 0; round < n_rounds; ++round) {
-    const long long chain_ll = ((long long)round * WARPS + warp) * gridDim.x + blockIdx.x;
+  for (int round = 0; round < n_rounds && warp != 0; ++round) {
+    const long long chain_ll = ((long long)round * CWARPS + (warp - 1)) * gridDim.x + blockIdx.x;
     const bool active = chain_ll < s.B;
     const int chain = (int)chain_ll;
     if (!active) {  // keep the ring moving: consume every row of this round's passes
-      for (uint32_t r = 0; r < passes_per_round * (uint32_t)N; ++r) {
-        (void)row_wait();
-        row_done();
+      for (uint32_t r = 0; r < passes_per_round * (uint32_t)NG; ++r) {
+        (void)grp_wait();
+        grp_done();
       }
       continue;
     }
@@ -422,21 +458,26 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_shadow_kernel(const __grid_c
         if (idx < N) sts_u8(sigp_s + idx, now);
       }
       // U: the double state follows the net change of the sweep
-      for (int ii = 0; ii < N; ++ii) {
-        const int i = (ii + (int)rot) % N;  // the row in this stage
-        const uint32_t rs = row_wait();
-        if ((sw4sel4(fl, i >> 5) >> (i & 31)) & 1u) {
-          double g[NV];
-          prod::load_row_s<NF64, TL>(rs + 16u * lane_o, rs + (uint32_t)LD::TAIL_OFF + (uint32_t)LD::TAIL_LANE * lane_o, g);
-          if ((sw4sel4(dn, i >> 5) >> (i & 31)) & 1u) {  // +1 -> -1: A <- A G
+      for (int gp = 0; gp < NG; ++gp) {
+        const int gi = cgi;
+        const uint32_t gs = grp_wait();
 #pragma unroll
-            for (int e = 0; e < NV; ++e) A[e] *= g[e];
-          } else {  // -1 -> +1: B <- B G
+        for (int sl = 0; sl < GROUP; ++sl) {
+          const int i = GROUP * gi + sl;
+          if (i < N && ((sw4sel4(fl, i >> 5) >> (i & 31)) & 1u)) {
+            const uint32_t rs = gs + (uint32_t)(sl * row64);
+            double g[NV];
+            prod::load_row_s<NF64, TL>(rs + 16u * lane_o, rs + (uint32_t)LD::TAIL_OFF + (uint32_t)LD::TAIL_LANE * lane_o, g);
+            if ((sw4sel4(dn, i >> 5) >> (i & 31)) & 1u) {  // +1 -> -1: A <- A G
 #pragma unroll
-            for (int e = 0; e < NV; ++e) Bv[e] *= g[e];
+              for (int e = 0; e < NV; ++e) A[e] *= g[e];
+            } else {  // -1 -> +1: B <- B G
+#pragma unroll
+              for (int e = 0; e < NV; ++e) Bv[e] *= g[e];
+            }
           }
         }
-        row_done();
+        grp_done();
       }
       rescale64(A, Bv);
       park_store(A, Bv);
@@ -477,25 +518,43 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_shadow_kernel(const __grid_c
           const double nrm = prod::warp_prod(nl);
           double off_l = 0.0;
           const int myidx = (lane_o >> 1) & 7;
-          for (int base = 0; base < N; base += 8) {
+          constexpr int GPB = 8 / GROUP;  // groups per butterfly of 8 sites
+          static_assert(GPB * GROUP == 8, "GROUP must divide 8");
+          for (int gp = 0; gp < NG; gp += GPB) {
             double v[8];
+            int gis[GPB];
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-              v[jj] = 1.0;
-              const int i = (base + jj + (int)rot) % N;
-              if (base + jj < N) {
-                const uint32_t rs = row_wait();
-                double g[NV];
-                prod::load_row_s<NF64, TL>(rs + 16u * lane_o, rs + (uint32_t)LD::TAIL_OFF + (uint32_t)LD::TAIL_LANE * lane_o, g);
-                const prod::LanePair<double> P = ((sw4sel4(dn, i >> 5) >> (i & 31)) & 1u) ? prod::lane_product<double, NV>(Bv, A, g)
-                                                                                : prod::lane_product<double, NV>(A, Bv, g);
-                v[jj] = P.a * P.b;
-                row_done();
+            for (int h = 0; h < GPB; ++h) {
+              gis[h] = -1;
+#pragma unroll
+              for (int sl = 0; sl < GROUP; ++sl) v[GROUP * h + sl] = 1.0;
+              if (gp + h < NG) {
+                const int gi = cgi;
+                gis[h] = gi;
+                const uint32_t gs = grp_wait();
+                // software pipeline: the loads of row sl + 1 are in flight while row sl is multiplied out
+                double g[2][NV];
+                prod::load_row_s<NF64, TL>(gs + 16u * lane_o, gs + (uint32_t)LD::TAIL_OFF + (uint32_t)LD::TAIL_LANE * lane_o, g[0]);
+#pragma unroll
+                for (int sl = 0; sl < GROUP; ++sl) {
+                  const int i = GROUP * gi + sl;
+                  if (sl + 1 < GROUP) {  // (a row past the table's end is a harmless read of the ring)
+                    const uint32_t rn = gs + (uint32_t)((sl + 1) * row64);
+                    prod::load_row_s<NF64, TL>(rn + 16u * lane_o, rn + (uint32_t)LD::TAIL_OFF + (uint32_t)LD::TAIL_LANE * lane_o, g[(sl + 1) & 1]);
+                  }
+                  if (i < N)
+                    v[GROUP * h + sl] = ((sw4sel4(dn, i >> 5) >> (i & 31)) & 1u) ? lane_product64<NV>(Bv, A, g[sl & 1])
+                                                                               : lane_product64<NV>(A, Bv, g[sl & 1]);
+                }
+                grp_done();
               }
             }
             const double tot = prod::bfly<double, 8>(v, lane_o);
-            const int mys = (base + myidx + (int)rot) % N;
-            if ((lane_o & 1) == 0 && lane_o < 16 && base + myidx < N) {
+            int mygi = gis[0];
+#pragma unroll
+            for (int h = 1; h < GPB; ++h) mygi = (myidx / GROUP == h) ? gis[h] : mygi;
+            const int mys = GROUP * mygi + (myidx % GROUP);
+            if ((lane_o & 1) == 0 && lane_o < 16 && mygi >= 0 && mys < N) {
               const double2 cst = rcd[mys];
               off_l += tot * (((sw4sel4(dn, mys >> 5) >> (mys & 31)) & 1u) ? cst.x : cst.y) / nrm;
             }
@@ -697,7 +756,7 @@ bool sweep_shadow_supported(const SweepKernelArgs &a, const ProdLayout &L) {
   const shadow::Layout Ls = shadow::make_layout(a.rbm.N, ss.mp32, L.row_bytes, E);
   if (Ls.total > 227 * 1024) return false;
   // the stream position is a 32-bit counter
-  const int64_t rounds = (a.B + (int64_t)num_sms() * shadow::WARPS - 1) / ((int64_t)num_sms() * shadow::WARPS);
+  const int64_t rounds = (a.B + (int64_t)num_sms() * shadow::CWARPS - 1) / ((int64_t)num_sms() * shadow::CWARPS);
   if (rounds * (a.n_discard + 2ll * a.chain_length) * a.rbm.N >= (1ll << 31)) return false;
   return true;
 }
@@ -706,7 +765,7 @@ template <int NF32, int TL>
 static int launch_shadow(cudaStream_t stream, const ProdArgs &pa, int give, int smem, double *park) {
   auto kern = shadow::sweep_shadow_kernel<NF32, TL>;
   NK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  const int64_t need = (pa.s.B + shadow::WARPS - 1) / shadow::WARPS;
+  const int64_t need = (pa.s.B + shadow::CWARPS - 1) / shadow::CWARPS;
   const int64_t cap = num_sms();
   kern<<<(int)(need < cap ? need : cap), shadow::THREADS, smem, stream>>>(pa, give, park);
   NK_LAUNCH_OK();

@@ -13,7 +13,7 @@ from netket_b200 import build as B  # noqa: E402
 
 name, flags = sys.argv[1], sys.argv[2:]
 out_dir = os.path.join(ROOT, "netket_b200", "lib", "variants")
-obj_dir = os.path.join(ROOT, "build", "variant_" + name)
+obj_dir = os.path.join("/tmp", "nkb200_variant_" + name)  # outside the tree: the snapshot sent to the GPU box stays small
 os.makedirs(out_dir, exist_ok=True)
 os.makedirs(obj_dir, exist_ok=True)
 objs = []
