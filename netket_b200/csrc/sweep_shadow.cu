@@ -87,10 +87,21 @@ __device__ __forceinline__ uint32_t sw4sel4(const uint32_t (&w)[4], int i) {
   return (i < 2) ? ((i == 0) ? w[0] : w[1]) : ((i == 2) ? w[2] : w[3]);
 }
 // all lanes poll, the exit is a warp vote: the loop is uniform for the compiler (no divergence to repair around the warp-wide
-// reductions of the hot loops)
+// reductions of the hot loops).  A poll is ~8 issued instructions; un-throttled, the polls of the producer (idle while the
+// consumers sweep) and of consumers waiting for the stream were 29 % of all instructions the kernel issued (ncu source page,
+// profiles/r02_shadow_polling.md), taken from the issue slots of the warps doing arithmetic: after FAST failed probes the
+// warp sleeps NS nanoseconds between probes.
+#ifndef NK_SH_PSLEEP
+#define NK_SH_PSLEEP 200
+#endif
+#ifndef NK_SH_CSLEEP
+#define NK_SH_CSLEEP 40
+#endif
+template <int FAST, int NS>
 __device__ __forceinline__ void mbar_wait_uniform(uint64_t *bar, uint32_t parity) {
   uint32_t done = 0;
-  do {
+  int tries = 0;
+  for (;;) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -100,25 +111,57 @@ __device__ __forceinline__ void mbar_wait_uniform(uint64_t *bar, uint32_t parity
         : "=r"(done)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
-  } while (!__all_sync(0xffffffffu, done != 0u));
+    if (__all_sync(0xffffffffu, done != 0u)) break;
+    if (NS > 0 && ++tries > FAST) __nanosleep(NS);
+  }
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// prod_e (X_e g_e + Y_e) with four interleaved accumulators (dependency depth ~ NV / 4 + 2 instead of NV / 2 + 1)
-template <int NV>
-__device__ __forceinline__ double lane_product64(const double (&X)[NV], const double (&Y)[NV], const double (&g)[NV]) {
-  double acc[4] = {1.0, 1.0, 1.0, 1.0};
+#ifdef NK_SH_PROFILE
+// build-time instrumentation (tools/build_variant.py prof -DNK_SH_PROFILE): cycles of warp 1 of CTA 0 per phase
+__device__ unsigned long long nk_sh_prof[16];
+#define NK_PROF_NOW() clock64()
+#define NK_PROF_ADD(slot, dt)                                              \
+  do {                                                                     \
+    if (blockIdx.x == 0 && warp == 1 && lane == 0) nk_sh_prof[slot] += (unsigned long long)(dt); \
+  } while (0)
+#else
+#define NK_PROF_NOW() 0ll
+#define NK_PROF_ADD(slot, dt) \
+  do {                        \
+    (void)(dt);               \
+  } while (0)
+#endif
+
+// prod_e (X_e g_e + Y_e) with four interleaved accumulators per row (dependency depth ~ NV / 4 + 2 instead of NV / 2 + 1),
+// two rows at once: the multiply tree of one row fills the dependency stalls of the other (the kernel runs at < 3 warps per
+// scheduler: the stalls are not hidden by other warps).  D0 / D1: the row's site is spin down (X = B, Y = A)
+template <int NV, bool D0, bool D1>
+__device__ __forceinline__ void lane_product64_x2(const double (&A)[NV], const double (&Bv)[NV], const double (&g0)[NV], const double (&g1)[NV],
+                                                  double &p0, double &p1) {
+  double a0[4] = {1.0, 1.0, 1.0, 1.0}, a1[4] = {1.0, 1.0, 1.0, 1.0};
 #pragma unroll
   for (int e = 0; e < NV; ++e) {
-    const double c = fma(X[e], g[e], Y[e]);
-    acc[e & 3] = e < 4 ? c : acc[e & 3] * c;
+    const double c0 = D0 ? fma(Bv[e], g0[e], A[e]) : fma(A[e], g0[e], Bv[e]);
+    const double c1 = D1 ? fma(Bv[e], g1[e], A[e]) : fma(A[e], g1[e], Bv[e]);
+    a0[e & 3] = e < 4 ? c0 : a0[e & 3] * c0;
+    a1[e & 3] = e < 4 ? c1 : a1[e & 3] * c1;
   }
-  if (NV == 1) return acc[0];
-  if (NV == 2) return acc[0] * acc[1];
-  if (NV == 3) return (acc[0] * acc[1]) * acc[2];
-  return (acc[0] * acc[1]) * (acc[2] * acc[3]);
+  if (NV == 1) {
+    p0 = a0[0];
+    p1 = a1[0];
+  } else if (NV == 2) {
+    p0 = a0[0] * a0[1];
+    p1 = a1[0] * a1[1];
+  } else if (NV == 3) {
+    p0 = (a0[0] * a0[1]) * a0[2];
+    p1 = (a1[0] * a1[1]) * a1[2];
+  } else {
+    p0 = (a0[0] * a0[1]) * (a0[2] * a0[3]);
+    p1 = (a1[0] * a1[1]) * (a1[2] * a1[3]);
+  }
 }
 
 // fp64 re-decision of one proposal (rare, ~3e-4 of the proposals).  The double state as of the last update is parked in the
@@ -287,7 +330,7 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_shadow_kernel(const __grid_c
     int gi = rotg;
     uint32_t st = 0, par = 0;  // parity of the `empty` phase to wait for (the stage's previous use); first waited at t = STAGES
     for (uint32_t t = 0; t < total_q; ++t) {
-      if (t >= (uint32_t)STAGES) mbar_wait_uniform(empty + st, par);
+      if (t >= (uint32_t)STAGES) mbar_wait_uniform<4, NK_SH_PSLEEP>(empty + st, par);
       if (lane == 0) {
         const uint32_t bytes = (uint32_t)(min(GROUP, N - GROUP * gi) * row64);
         mbar_expect_tx(full + st, bytes);
@@ -304,8 +347,11 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_shadow_kernel(const __grid_c
   // consumer side of the ring: stage, parity and table group of the next group in the stream, kept incrementally
   uint32_t cst = 0, cpar = 0;
   int cgi = rotg;
+  long long prof_wait = 0;
   auto grp_wait = [&]() -> uint32_t {  // wait for the next group of the stream; returns the shared address of its first row
-    mbar_wait_uniform(full + cst, cpar);
+    const long long pw0 = NK_PROF_NOW();
+    mbar_wait_uniform<2, NK_SH_CSLEEP>(full + cst, cpar);
+    prof_wait += NK_PROF_NOW() - pw0;
     return ring_s + cst * stage_bytes;
   };
   auto grp_done = [&]() {  // this warp has read the group's rows into registers (or skipped them)
@@ -444,8 +490,12 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_shadow_kernel(const __grid_c
 
     // ---- end of a sweep: U (always), outputs and E (recorded sweeps)
     int sweep_idx = 0;
+    long long prof_s0 = NK_PROF_NOW();
     auto end_of_sweep = [&]() {
       __syncwarp();
+      const long long pt0 = NK_PROF_NOW();
+      NK_PROF_ADD(0, pt0 - prof_s0);
+      const long long pwt0 = prof_wait;
       double A[NV], Bv[NV];
       park_load(A, Bv);
       uint32_t fl[4], dn[4];
@@ -461,19 +511,24 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_shadow_kernel(const __grid_c
       for (int gp = 0; gp < NG; ++gp) {
         const int gi = cgi;
         const uint32_t gs = grp_wait();
+        // the rows of a group sit in one 32-bit word of the masks (GROUP divides 32; bits past N are zero)
+        const int i0 = GROUP * gi;
+        const uint32_t flb = (sw4sel4(fl, i0 >> 5) >> (i0 & 31)) & ((1u << GROUP) - 1u);
+        const uint32_t dnb = sw4sel4(dn, i0 >> 5) >> (i0 & 31);
+        if (flb != 0u) {
 #pragma unroll
-        for (int sl = 0; sl < GROUP; ++sl) {
-          const int i = GROUP * gi + sl;
-          if (i < N && ((sw4sel4(fl, i >> 5) >> (i & 31)) & 1u)) {
-            const uint32_t rs = gs + (uint32_t)(sl * row64);
-            double g[NV];
-            prod::load_row_s<NF64, TL>(rs + 16u * lane_o, rs + (uint32_t)LD::TAIL_OFF + (uint32_t)LD::TAIL_LANE * lane_o, g);
-            if ((sw4sel4(dn, i >> 5) >> (i & 31)) & 1u) {  // +1 -> -1: A <- A G
+          for (int sl = 0; sl < GROUP; ++sl) {
+            if ((flb >> sl) & 1u) {
+              const uint32_t rs = gs + (uint32_t)(sl * row64);
+              double g[NV];
+              prod::load_row_s<NF64, TL>(rs + 16u * lane_o, rs + (uint32_t)LD::TAIL_OFF + (uint32_t)LD::TAIL_LANE * lane_o, g);
+              if ((dnb >> sl) & 1u) {  // +1 -> -1: A <- A G
 #pragma unroll
-              for (int e = 0; e < NV; ++e) A[e] *= g[e];
-            } else {  // -1 -> +1: B <- B G
+                for (int e = 0; e < NV; ++e) A[e] *= g[e];
+              } else {  // -1 -> +1: B <- B G
 #pragma unroll
-              for (int e = 0; e < NV; ++e) Bv[e] *= g[e];
+                for (int e = 0; e < NV; ++e) Bv[e] *= g[e];
+              }
             }
           }
         }
@@ -481,6 +536,10 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_shadow_kernel(const __grid_c
       }
       rescale64(A, Bv);
       park_store(A, Bv);
+      const long long pt1 = NK_PROF_NOW();
+      NK_PROF_ADD(2, pt1 - pt0);
+      NK_PROF_ADD(8, prof_wait - pwt0);
+      const long long pwt1 = prof_wait;
       const int sw = sweep_idx - s.n_discard;
       ++sweep_idx;
       if (sw >= 0) {
@@ -532,19 +591,26 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_shadow_kernel(const __grid_c
                 const int gi = cgi;
                 gis[h] = gi;
                 const uint32_t gs = grp_wait();
-                // software pipeline: the loads of row sl + 1 are in flight while row sl is multiplied out
-                double g[2][NV];
-                prod::load_row_s<NF64, TL>(gs + 16u * lane_o, gs + (uint32_t)LD::TAIL_OFF + (uint32_t)LD::TAIL_LANE * lane_o, g[0]);
+                const int i0 = GROUP * gi;
+                const uint32_t dnb = sw4sel4(dn, i0 >> 5) >> (i0 & 31);  // spins of the group's rows (one word: GROUP divides 32)
+                const int nval = N - i0;                                  // rows of the group inside the table
+                // rows in pairs: both rows' loads first, then the two products interleaved
+                static_assert(GROUP % 2 == 0, "rows are paired");
 #pragma unroll
-                for (int sl = 0; sl < GROUP; ++sl) {
-                  const int i = GROUP * gi + sl;
-                  if (sl + 1 < GROUP) {  // (a row past the table's end is a harmless read of the ring)
-                    const uint32_t rn = gs + (uint32_t)((sl + 1) * row64);
-                    prod::load_row_s<NF64, TL>(rn + 16u * lane_o, rn + (uint32_t)LD::TAIL_OFF + (uint32_t)LD::TAIL_LANE * lane_o, g[(sl + 1) & 1]);
+                for (int sl = 0; sl < GROUP; sl += 2) {
+                  double g0[NV], g1[NV];  // (a row past the table's end is a harmless read of the ring)
+                  const uint32_t r0 = gs + (uint32_t)(sl * row64), r1 = r0 + (uint32_t)row64;
+                  prod::load_row_s<NF64, TL>(r0 + 16u * lane_o, r0 + (uint32_t)LD::TAIL_OFF + (uint32_t)LD::TAIL_LANE * lane_o, g0);
+                  prod::load_row_s<NF64, TL>(r1 + 16u * lane_o, r1 + (uint32_t)LD::TAIL_OFF + (uint32_t)LD::TAIL_LANE * lane_o, g1);
+                  double p0, p1;
+                  switch ((dnb >> sl) & 3u) {
+                    case 0u: lane_product64_x2<NV, false, false>(A, Bv, g0, g1, p0, p1); break;
+                    case 1u: lane_product64_x2<NV, true, false>(A, Bv, g0, g1, p0, p1); break;
+                    case 2u: lane_product64_x2<NV, false, true>(A, Bv, g0, g1, p0, p1); break;
+                    default: lane_product64_x2<NV, true, true>(A, Bv, g0, g1, p0, p1); break;
                   }
-                  if (i < N)
-                    v[GROUP * h + sl] = ((sw4sel4(dn, i >> 5) >> (i & 31)) & 1u) ? lane_product64<NV>(Bv, A, g[sl & 1])
-                                                                               : lane_product64<NV>(A, Bv, g[sl & 1]);
+                  if (sl < nval) v[GROUP * h + sl] = p0;
+                  if (sl + 1 < nval) v[GROUP * h + sl + 1] = p1;
                 }
                 grp_done();
               }
@@ -585,6 +651,10 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_shadow_kernel(const __grid_c
       }
       refresh_shadow(A, Bv);
       __syncwarp();
+      prof_s0 = NK_PROF_NOW();
+      NK_PROF_ADD(4, prof_s0 - pt1);
+      NK_PROF_ADD(9, prof_wait - pwt1);
+      NK_PROF_ADD(7, 1);
     };
 
     // ---- S: the proposal loop of sweep_fast.cu on the shadow, with the fp64 re-decision inside the band
@@ -628,8 +698,10 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_shadow_kernel(const __grid_c
         const int kend = k + min(nb - k, sweep_size - in_sweep);
         const int k0 = k;
         bool need_exact = false;
+        uint4 nrec = lds128u(rec_s + 16u * k);
         for (; k < kend; ++k) {
-          const uint4 rec = lds128u(rec_s + 16u * k);
+          const uint4 rec = nrec;  // the next record is fetched a proposal ahead (past the last one: the neighbouring slot, unused)
+          nrec = lds128u(rec_s + 16u * (k + 1));
           const uint32_t sdown = lds_u8(rec.y);
           float2 g2[NPA];
           float gt = 1.0f;
@@ -677,8 +749,11 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_shadow_kernel(const __grid_c
             u = reinterpret_cast<const double *>(s.stream_u)[(size_t)(tt + k) * s.B + chain];
           else
             u = uniform_from_words<double>(philox_words(s.seed, s.t0 + (uint64_t)(tt + k), gchain, STREAM_STEP));
+          const long long pe0 = NK_PROF_NOW();
           const bool ok = pw > 0.0 ? __any_sync(FULL, exact_accept<NF64, TL>(p, park, sig_s, sigp_s, site, sdown != 0u, u, pw, lane_o)) != 0 : true;
           forced = ok ? 2 : 1;
+          NK_PROF_ADD(1, NK_PROF_NOW() - pe0);
+          NK_PROF_ADD(6, 1);
           continue;
         }
         if (in_sweep == sweep_size) {
@@ -798,3 +873,12 @@ int sweep_shadow(cudaStream_t stream, const ProdArgs &pa, int give, double *park
 }
 
 }  // namespace nk
+
+#ifdef NK_SH_PROFILE
+extern "C" int nk_debug_shadow_profile(unsigned long long *out16) {
+  unsigned long long z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(out16, nk::shadow::nk_sh_prof, sizeof(z)) != cudaSuccess) return -1;
+  return cudaMemcpyToSymbol(nk::shadow::nk_sh_prof, z, sizeof(z)) == cudaSuccess ? 0 : -1;
+}
+#endif

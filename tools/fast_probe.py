@@ -64,6 +64,18 @@ def main():
     n = a.chains * a.cl
     print(f"path={a.path} dtype={a.dtype} chains={a.chains} cl={a.cl} std={a.std}: {ms:.3f} ms/launch (min {min(times):.3f}), "
           f"{n / ms * 1e3:.4g} samples/s, acceptance={st.acceptance:.4f}")
+    try:  # -DNK_SH_PROFILE builds: cycles of one warp per phase of the fp64 shadow kernel
+        import ctypes
+        from netket_b200 import _lib as _L
+        fn = _L.lib().nk_debug_shadow_profile
+        buf = (ctypes.c_ulonglong * 16)()
+        if fn(buf) == 0 and buf[7]:
+            v = [int(x) for x in buf]
+            ns = v[7]
+            print(f"  shadow profile (cycles per sweep of one warp, {ns} sweeps): S={v[0] / ns:.0f} exact={v[1] / ns:.0f} "
+                  f"({v[6] / ns:.3f}/sweep) U={v[2] / ns:.0f} (ring wait {v[8] / ns:.0f}) E+out={v[4] / ns:.0f} (ring wait {v[9] / ns:.0f})")
+    except AttributeError:
+        pass
     # accuracy on the first chains
     k = min(a.check, a.chains)
     s_np = samples[:k].cpu().numpy()
