@@ -245,8 +245,9 @@ def measure(nk, torch, dist, rank, ws, device, dtype, steps, warmup):
     achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
     peak = microbench(0)
     kernel = ("sweep_fast_kernel<3,1> (fused sweep + E_loc + statistics, fp32 LocalRule specialisation)" if dtype == "float32"
-              else "sweep_prod_kernel<double,6,1,LocalRule> (fused sweep + E_loc; 66 of 100 table rows resident in shared memory, "
-                   "the others read through L2)")
+              else "sweep_shadow_kernel<3,1> (fused sweep + E_loc + statistics: accept / reject on an fp32 shadow of the state against "
+                   "a resident fp32 table, re-decided in fp64 inside the shadow's error band; the fp64 state follows the net flips of "
+                   "each sweep and the fp64 local energy is formed from double rows streamed through a TMA ring)")
     roofline = {"bound": "smem", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None,
                 "traffic_note": "DRAM bytes are not measurable inside bench.py (no profiler in the timed run); the ncu captures "
@@ -259,18 +260,24 @@ def measure(nk, torch, dist, rank, ws, device, dtype, steps, warmup):
                                "(its HBM copy number does not bound this path: HBM traffic is ~120 B/sample)",
                 "method": "CUDA events on the launching stream around nk_sweep, minus the separately timed theta kernel"}
     if dtype == "float64":
-        # competing bounds of the fp64 kernel, measured in the same run: the FP64 pipe (one DFMA + one DMUL per table element
-        # and row operation, one more DMUL per element of an accepted move) and the L2 reads of the non-resident rows
+        # competing bounds of the fp64 kernel, measured in the same run: the FP64 pipe (E: one DFMA + one DMUL per table element
+        # of every site; U: one DMUL per element of every net-flipped site, a fraction (1 - exp(-2 acc)) / 2 of the sites) and the
+        # L2 -> shared stream of the double table (two passes per sample and CTA, shared by the 11 chains a CTA sweeps at a time)
+        import math
         dp_peak_inst = microbench(4) / 2.0  # G lane-instructions/s (the microbenchmark counts 2 flop per DFMA)
         acc = float(vs.sampler_state.acceptance)
-        dp_per_sample = N_SITES * N_HIDDEN * (2.0 + acc + 2.0)
+        net_flip = 0.5 * (1.0 - math.exp(-2.0 * acc))
+        dp_per_sample = N_SITES * N_HIDDEN * (2.0 + net_flip)
         dp_ach = CHAINS_PER_GPU * CHAIN_LENGTH * dp_per_sample / (ms_kernel * 1e-3) / 1e9
         l2_peak = microbench(1)
-        l2_bytes = (1.0 - 66.0 / 100.0) * bytes_per_sample(esz)
+        l2_bytes = 2.0 * N_SITES * N_HIDDEN * 8.0 / 11.0
         roofline["competing"] = {
             "fp64_pipe": {"achieved": dp_ach, "peak": dp_peak_inst, "unit": "G lane-instructions/s", "frac": dp_ach / dp_peak_inst},
-            "l2": {"achieved": CHAINS_PER_GPU * CHAIN_LENGTH * l2_bytes / (ms_kernel * 1e-3) / 1e9, "peak": l2_peak, "unit": "GB/s",
-                   "frac": CHAINS_PER_GPU * CHAIN_LENGTH * l2_bytes / (ms_kernel * 1e-3) / 1e9 / l2_peak}}
+            "l2_stream": {"achieved": CHAINS_PER_GPU * CHAIN_LENGTH * l2_bytes / (ms_kernel * 1e-3) / 1e9, "peak": l2_peak, "unit": "GB/s",
+                          "frac": CHAINS_PER_GPU * CHAIN_LENGTH * l2_bytes / (ms_kernel * 1e-3) / 1e9 / l2_peak},
+            "note": "neither bound binds: at 168 registers per thread (26 doubles of state + two rows in flight) the kernel runs 3 warps "
+                    "per scheduler and is bound by dependent-issue latency (ncu: issue slots 45 % busy, stall 'wait' 2.2 cycles per "
+                    "instruction; profiles/r02_ncu_summary.txt)"}
     return {"value": value, "ms_per_step": ms / steps, "launches": launches, "roofline": roofline, "stats": result["stats"],
             "acceptance": vs.sampler_state.acceptance, "params": (W, b, a)}
 

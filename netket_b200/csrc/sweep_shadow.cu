@@ -50,6 +50,7 @@ constexpr int BAND = 64;         // fixed-point units (2^-19 in log2): decisions
 constexpr float SH_EXP_RANGE = 100.0f;
 constexpr int SIG_STRIDE = 128;  // spin bytes per warp
 constexpr int WSTAT = 12;
+constexpr int REC_SLOT = 33 * 16;  // 32 proposal records per warp + one never-written entry: the record prefetch runs one past the last
 
 struct Layout {
   int g32, rcx, rcd, edges, rec, sig, sigp, wstat, ring, bars, red, total;
@@ -66,7 +67,7 @@ __host__ __device__ inline Layout make_layout(int N, int MP32, int row64, int E)
   L.edges = o;
   o += (2 * E + 15) & ~15;
   L.rec = o;
-  o += WARPS * 512;
+  o += WARPS * REC_SLOT;
   L.sig = o;
   o += WARPS * SIG_STRIDE;
   L.sigp = o;
@@ -105,7 +106,11 @@ __device__ __forceinline__ void mbar_wait_uniform(uint64_t *bar, uint32_t parity
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
+#ifdef NK_SH_TRYWAIT  // developer switch (compute-sanitizer racecheck experiment, profiles/README.md)
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+#else
         "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"  // non-blocking probe: try_wait suspends the thread for a
+#endif
         "selp.u32 %0, 1, 0, p;\n"                                     // system-chosen time (measured: ~0.5 us per ring hand-over)
         "}\n"
         : "=r"(done)
@@ -304,7 +309,7 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_shadow_kernel(const __grid_c
   const int n_b = CL / l_block, half = CL / 2;
   uint32_t g_s = smem_u32(G32);
   uint32_t lane16 = 16u * lane, tailoff = 512u * NF32 + 4u * TL * lane;
-  uint32_t rec_s = smem_u32(smem + L.rec) + 512u * warp;
+  uint32_t rec_s = smem_u32(smem + L.rec) + (uint32_t)REC_SLOT * warp;
   uint32_t sig_s = smem_u32(smem + L.sig) + (uint32_t)SIG_STRIDE * warp;
   uint32_t sigp_s = smem_u32(smem + L.sigp) + (uint32_t)SIG_STRIDE * warp;
   const uint32_t ring_s = smem_u32(smem + L.ring);
@@ -700,7 +705,7 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_shadow_kernel(const __grid_c
         bool need_exact = false;
         uint4 nrec = lds128u(rec_s + 16u * k);
         for (; k < kend; ++k) {
-          const uint4 rec = nrec;  // the next record is fetched a proposal ahead (past the last one: the neighbouring slot, unused)
+          const uint4 rec = nrec;  // the next record is fetched a proposal ahead (past the last one: the slot's spare entry, unused)
           nrec = lds128u(rec_s + 16u * (k + 1));
           const uint32_t sdown = lds_u8(rec.y);
           float2 g2[NPA];

@@ -38,11 +38,17 @@ def record(what, tol, err):
     try:
         os.makedirs(os.path.dirname(_LOG), exist_ok=True)
         with open(_LOG, "a") as fh:
-            fh.write(json.dumps({"what": what or os.environ.get("PYTEST_CURRENT_TEST", ""), "tol": tol, "n": int(err.size),
+            fh.write(json.dumps({"what": _label(what), "tol": tol, "n": int(err.size),
                                  "max_rel": float(err.max()) if err.size else 0.0,
                                  "median_rel": float(np.median(err)) if err.size else 0.0}) + "\n")
     except OSError:
         pass
+
+
+def _label(what):
+    """Test id (+ the caller's tag): unique per parametrised case, so that the log can be de-duplicated run after run."""
+    test = os.environ.get("PYTEST_CURRENT_TEST", "").replace(" (call)", "")
+    return f"{test} [{what}]" if what and test else (what or test)
 
 
 def rel_err(x, ref, floor_frac):
@@ -59,7 +65,7 @@ def assert_rel(x, ref, tol, what=""):
     try:
         os.makedirs(os.path.dirname(_LOG), exist_ok=True)
         with open(_LOG, "a") as fh:
-            fh.write(json.dumps({"what": what or os.environ.get("PYTEST_CURRENT_TEST", ""), "tol": tol, "n": int(ref.size),
+            fh.write(json.dumps({"what": _label(what), "tol": tol, "n": int(ref.size),
                                  "max_rel": float(err.max()) if err.size else 0.0,
                                  "median_rel": float(np.median(err)) if err.size else 0.0}) + "\n")
     except OSError:

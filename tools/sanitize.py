@@ -1,6 +1,6 @@
 """Small launches of every kernel family, for compute-sanitizer (memcheck / racecheck / synccheck / initcheck):
 
-    compute-sanitizer --tool racecheck python tools/sanitize.py
+    compute-sanitizer --tool racecheck python tools/sanitize.py [case indices]
 """
 import os, sys
 import numpy as np, torch
@@ -26,12 +26,20 @@ def run(dtype, rule, L, n_dim, alpha, op_kind, path=0, B=40, CL=2, grad=False):
     print(f"ok {np.dtype(dtype).name} {rule} N={N} M={int(alpha * N)} {op_kind} path={path}: E = {eloc.mean().item():.4f} / {e2.mean().item():.4f}")
 
 
-run(np.float32, "local", 6, 2, 4, "ising", grad=True)            # sweep_fast + theta tcgen05 + forces tcgen05
-run(np.float32, "local", 6, 2, 4, "ising", path=3)               # sweep_prod f32 local
-run(np.float64, "local", 6, 2, 4, "ising", grad=True)            # sweep_prod f64 local + theta DMMA + forces DMMA
-run(np.float64, "exchange", 6, 2, 2, "heis")                     # sweep_prod f64 exchange + LocalOperator E_loc
-run(np.float32, "exchange", 12, 1, 2, "heis")                    # sweep_prod f32 exchange
-run(np.float32, "local", 20, 1, 32, "ising")                     # MULTI (2 warps per chain)
-run(np.float64, "local", 16, 1, 40, "ising")                     # MULTI fp64
-run(np.float64, "local", 14, 2, 2, "ising")                      # N = 196: rows through L2
-run(np.float64, "local", 6, 2, 4, "ising", path=1)               # theta-form kernels
+CASES = [
+    lambda: run(np.float32, "local", 6, 2, 4, "ising", grad=True),  # sweep_fast + theta tcgen05 + forces tcgen05
+    lambda: run(np.float32, "local", 6, 2, 4, "ising", path=3),  # sweep_prod f32 local
+    lambda: run(np.float64, "local", 6, 2, 4, "ising", grad=True),  # sweep_prod f64 local + theta DMMA + forces DMMA
+    lambda: run(np.float64, "exchange", 6, 2, 2, "heis"),  # sweep_prod f64 exchange + LocalOperator E_loc
+    lambda: run(np.float32, "exchange", 12, 1, 2, "heis"),  # sweep_prod f32 exchange
+    lambda: run(np.float32, "local", 20, 1, 32, "ising"),  # MULTI (2 warps per chain)
+    lambda: run(np.float64, "local", 16, 1, 40, "ising"),  # MULTI fp64
+    lambda: run(np.float64, "local", 14, 2, 2, "ising"),  # N = 196: rows through L2
+    lambda: run(np.float64, "local", 6, 2, 4, "ising", path=1),  # theta-form kernels
+    lambda: run(np.float64, "local", 10, 2, 4, "ising", B=24),  # cfg-3 shape: fp64 shadow kernel (TMA ring, producer warp, parked state)
+    lambda: run(np.float32, "local", 10, 2, 4, "ising", B=24),  # cfg-3 shape: sweep_fast <3, 1>
+]
+only = [int(x) for x in sys.argv[1:]]  # e.g. `python tools/sanitize.py 9 10`: only those cases
+for idx, case in enumerate(CASES):
+    if not only or idx in only:
+        case()
