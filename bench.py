@@ -423,6 +423,28 @@ def measure_strong_and_others(nk, torch, dist, rank, ws, device, steps):
                       "note": "step time, against the shared-memory read bandwidth (the resident rows' bound)"}
     others["cfg4_j1j2_f64_exchange"] = r4
     strong["cfg4_f64_262144_samples_total"] = {k2: r4[k2] for k2 in ("value", "unit", "ms_per_step", "steps", "chains_total", "chain_length")}
+    # K4: Ising get_conn_padded on the cfg-3 batch - the path's HBM-write-bound kernel - and `statistics` on
+    # given data, against the HBM copy bandwidth the driver measured (MEASURED_PEAKS.json) or the profiling guide's fallback
+    try:
+        hbm_peak, hbm_src = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        hbm_peak, hbm_src = 7700.0, "fallback: B200_PROFILING.md nominal 7.7 TB/s (MEASURED_PEAKS.json absent)"
+    g3 = nk.graph.Hypercube(L_SIDE, 2, pbc=True)
+    hi3 = nk.hilbert.Spin(0.5, N_SITES)
+    op3 = nk.operator.Ising(hi3, g3, h=H_FIELD)
+    x3 = hi3.random_state(1, CHAINS_PER_GPU, device=device)
+    ms_conn = timed_steps(torch, dist, 1, lambda: op3.get_conn_padded(x3), 5, 3) / 5
+    by = CHAINS_PER_GPU * (N_SITES + 1) * N_SITES + CHAINS_PER_GPU * (N_SITES + 1) * 8 + CHAINS_PER_GPU * N_SITES
+    others["k4_ising_get_conn_padded_cfg3"] = {
+        "ms": ms_conn, "batch": CHAINS_PER_GPU, "n_conn": N_SITES + 1,
+        "roofline": {"bound": "hbm", "achieved": by / (ms_conn * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": by / (ms_conn * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": by, "peak_source": hbm_src,
+                     "kernel": "ising_conn_kernel (sigma' [B, N+1, N] int8 + mels [B, N+1] fp64 written, sigma read)"}}
+    e3 = torch.randn(CHAINS_PER_GPU, CHAIN_LENGTH, dtype=torch.float64, device=device)
+    ms_stat = timed_steps(torch, dist, 1, lambda: nk.stats.statistics(e3), 5, 3) / 5
+    others["k6_statistics_on_given_data"] = {"ms": ms_stat, "shape": [CHAINS_PER_GPU, CHAIN_LENGTH],
+                                            "note": "two-pass stats_partial_kernel + all-reduce + one host read; inside a step the sums "
+                                                    "come from the sweep kernel's epilogue instead"}
     return strong, others
 
 

@@ -39,6 +39,7 @@ class Dispatcher:
         self.__name__ = name
         self.__doc__ = doc
         self._methods = []  # (signature: tuple of tuples of types, precedence, fn)
+        self._cache = {}    # argument types -> resolved method (as plum: resolution runs once per type tuple)
 
     def dispatch(self, fn=None, *, precedence=0):
         if fn is None:
@@ -48,6 +49,7 @@ class Dispatcher:
         sig = tuple(_norm(p.annotation) for p in params)
         self._methods = [m for m in self._methods if m[0] != sig]  # re-registration overrides
         self._methods.append((sig, precedence, fn))
+        self._cache.clear()
         return self
 
     @staticmethod
@@ -60,6 +62,13 @@ class Dispatcher:
         return all(all(any(issubclass(x, y) for y in tb) for x in ta) for ta, tb in zip(a, b))
 
     def resolve(self, *args):
+        key = tuple(type(a) for a in args)
+        fn = self._cache.get(key)
+        if fn is None:
+            fn = self._cache[key] = self._resolve(args)
+        return fn
+
+    def _resolve(self, args):
         cands = [m for m in self._methods if self._accepts(m[0], args)]
         if not cands:
             raise NotImplementedError(f"{self.__name__}: no method registered for ({', '.join(type(a).__name__ for a in args)})")
