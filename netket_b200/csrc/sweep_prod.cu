@@ -354,7 +354,6 @@ bool sweep_prod_supported(const SweepKernelArgs &a) {
   ProdLayout L;
   if (a.rbm.N > 1024 || !prod_shape(a.rbm.M, a.rbm.dtype, a.rule, &ps)) return false;
   if (a.rule == NK_RULE_EXCHANGE && (a.n_clusters < 1 || a.n_clusters > 32 * PROD_HOP_WORDS)) return false;
-  if (a.rule == NK_RULE_EXCHANGE && a.cluster_probs != nullptr) return false;  // weighted cluster choice: theta-form kernel
   if (a.eloc_kind == 1 && a.ising.n_edges > 8192) return false;
   if (a.B >= (1ll << 31) || (int64_t)(a.n_discard + a.chain_length) * a.sweep_size >= (1ll << 31)) return false;  // 32-bit counters
   return prod_layout(a, ps, &L);

@@ -434,6 +434,7 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
   const Rc *rctab = reinterpret_cast<const Rc *>(aux + L.rc_off);
   const int *lgtab = reinterpret_cast<const int *>(aux + L.lg_off);
   const uint16_t *cl = reinterpret_cast<const uint16_t *>(aux + L.cl_off);
+  const double *cprob = RULE == NK_RULE_EXCHANGE ? s.cluster_probs : nullptr;  // ExchangeRule(probabilities=) weights, or NULL
   const uint8_t *adjdeg = aux + L.adjdeg_off;
   const uint32_t *adj = reinterpret_cast<const uint32_t *>(aux + L.adj_off);
   const uint16_t *edges = reinterpret_cast<const uint16_t *>(aux + L.edges_off);
@@ -955,11 +956,53 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
               stoggle(site);
             }
           } else {
-            // ExchangeRule.transition (rules/exchange.py:143-184), probabilities=None
-            if (n_hop > 0) {
+            // ExchangeRule.transition (rules/exchange.py:143-184): uniform over the hoppable clusters, or
+            // (probabilities=, :86-123,155-160) by inverse CDF over their weights
+            int csel = -1;
+            double w_hop = 0.0;  // weighted rule: total weight of the hoppable clusters
+            if (cprob != nullptr) {
+              // lane l owns clusters 64 l .. 64 l + 63 (words 2l, 2l+1): its weight, an inclusive scan over the lanes, then the
+              // first cluster (in cluster order) whose running weight reaches r = W (w0 + 1/2) / 2^32  (jax.random.choice:
+              // searchsorted(cumsum(p), r))
+              const uint2 hw = *reinterpret_cast<const uint2 *>(hopw + 2 * lane);
+              double wl = 0.0;
+              for (uint32_t bts = hw.x; bts != 0u; bts &= bts - 1u) wl += cprob[64 * lane + __ffs(bts) - 1];
+              for (uint32_t bts = hw.y; bts != 0u; bts &= bts - 1u) wl += cprob[64 * lane + 32 + __ffs(bts) - 1];
+              double incl = wl;
+#pragma unroll
+              for (int dd = 1; dd < 32; dd <<= 1) {
+                const double t = __shfl_up_sync(FULL, incl, dd);
+                if (lane >= dd) incl += t;
+              }
+              w_hop = __shfl_sync(FULL, incl, 31);
+              if (w_hop > 0.0) {
+                const double r = w_hop * (((double)w0 + 0.5) * 2.3283064365386963e-10);
+                const uint32_t bal = __ballot_sync(FULL, (hw.x | hw.y) != 0u && incl >= r);
+                // (rounding can leave r above the last running sum: the last hoppable cluster, as searchsorted clipped)
+                const uint32_t any = __ballot_sync(FULL, (hw.x | hw.y) != 0u);
+                const int src = bal != 0u ? __ffs(bal) - 1 : 31 - __clz(any);
+                int cidx = 0;
+                if (lane == src) {
+                  double run = incl - wl;
+                  int last = 0;
+                  bool found = false;
+                  for (uint32_t bts = hw.x; bts != 0u && !found; bts &= bts - 1u) {
+                    last = 64 * lane + __ffs(bts) - 1;
+                    run += cprob[last];
+                    found = run >= r;
+                  }
+                  for (uint32_t bts = hw.y; bts != 0u && !found; bts &= bts - 1u) {
+                    last = 64 * lane + 32 + __ffs(bts) - 1;
+                    run += cprob[last];
+                    found = run >= r;
+                  }
+                  cidx = last;
+                }
+                csel = __shfl_sync(FULL, cidx, src);
+              }
+            } else if (n_hop > 0) {
               const int kth = (int)__umulhi(w0, (uint32_t)n_hop);
               // ---- the kth hoppable cluster in cluster order: lane l owns words 2l, 2l+1
-              int csel;
               {
                 const uint2 hw = *reinterpret_cast<const uint2 *>(hopw + 2 * lane);
                 const int c0 = __popc(hw.x), cnt = c0 + __popc(hw.y);
@@ -976,6 +1019,8 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
                 if (lane == src) cidx = kk < c0 ? 64 * lane + kth_set_bit(hw.x, kk) : 64 * lane + 32 + kth_set_bit(hw.y, kk - c0);
                 csel = __shfl_sync(FULL, cidx, src);
               }
+            }
+            if (csel >= 0) {
               const int si = cl[2 * csel], sj = cl[2 * csel + 1];
               const bool ineg = sbit(si) != 0;
               const int sp = ineg ? si : sj;  // sigma = -1 -> +1: multiplies B
@@ -983,6 +1028,7 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
               // ---- n_hop(sigma'): every other cluster containing si or sj toggles
               uint32_t ei = 0xffffffffu, ej = 0xffffffffu;
               int n1 = 0, n0 = 0;
+              double w_hop_p = 0.0;
               {
                 const bool vi = lane < (int)adjdeg[si];
                 if (vi) ei = adj[si * PROD_ADJ_MAX + lane];
@@ -996,11 +1042,21 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
                 const uint32_t bj = uj ? (hopw[(ej & 0xffffu) >> 5] >> (ej & 31u)) & 1u : 0u;
                 n1 = __popc(__ballot_sync(FULL, bi != 0)) + __popc(__ballot_sync(FULL, bj != 0));
                 n0 = __popc(__ballot_sync(FULL, ui && bi == 0)) + __popc(__ballot_sync(FULL, uj && bj == 0));
+                if (cprob != nullptr) {  // W(sigma') = W(sigma) -+ the weights of the clusters that stop / start being hoppable
+                  double dw = 0.0;
+                  if (ui) dw += bi ? -cprob[ei & 0xffffu] : cprob[ei & 0xffffu];
+                  if (uj) dw += bj ? -cprob[ej & 0xffffu] : cprob[ej & 0xffffu];
+                  w_hop_p = w_hop + warp_sum(dw);
+                }
               }
               const int nhp = n_hop - n1 + n0;
               const Rc &rp = rctab[sp];
               const Rc &rm = rctab[sm];
-              const int cfix = rp.fx + rp.fy + rm.fx - rm.fy + lgtab[n_hop] - lgtab[nhp];
+              // log_prob_corr = log n(sigma) - log n(sigma')  (:177-182), with the total weights in place of the counts
+              const double corr_w = cprob != nullptr ? log(w_hop) - log(w_hop_p) : 0.0;
+              const int corr_fx = cprob != nullptr ? __double2int_rn(corr_w * 1.4426950408889634 * (double)inv_pw * (double)PROD_FX_SCALE)
+                                                   : lgtab[n_hop] - lgtab[nhp];
+              const int cfix = rp.fx + rp.fy + rm.fx - rm.fy + corr_fx;
               V g[NV], t[NV];
               fetch(sm, g);
 #pragma unroll
@@ -1020,7 +1076,7 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
                   acc = false;
                 else
                   acc = exact_decide(exact_logratio(lp_val(P), lane_norm()), rp.xn + rp.yn + rm.xn - rm.yn, __shfl_sync(FULL, u_l, k), pw,
-                                     log((double)n_hop) - log((double)nhp));
+                                     cprob != nullptr ? corr_w : log((double)n_hop) - log((double)nhp));
               } else {
                 acc = thr < X;
               }

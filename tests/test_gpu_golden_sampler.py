@@ -32,8 +32,6 @@ def test_cuda_chain_equals_reference_source_chain_fp64(cuda, tag, path):
     import netket_b200 as nk
 
     c = load_case(tag)
-    if c["probs"] is not None and path == "product-form":
-        pytest.skip("weighted cluster choice runs on the theta-form kernel (NK_PATH_AUTO selects it)")
     hi, sa = _sampler(nk, c)
     var = {"params": {"Dense": {"kernel": torch.from_numpy(c["W"]).cuda(), "bias": torch.from_numpy(c["b"]).cuda()},
                       "visible_bias": torch.from_numpy(c["a"]).cuda()}}

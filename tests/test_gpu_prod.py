@@ -116,6 +116,54 @@ def test_prod_sweep_size_discard_and_machine_pow(cuda):
     assert np.array_equal(samples.cpu().numpy(), ref["samples"])
 
 
+@pytest.mark.parametrize("L,n_dim,alpha,std,total_sz,d_max,probs", [
+    (12, 1, 2, 0.3, 0, 2, [0.7, 0.3]), (6, 2, 2, 0.05, 0, 2, [1.0, 2.5]), (10, 2, 4, 0.02, 0, 1, None), (22, 1, 2, 0.1, 1, 3, [3.0, 1.0, 0.25])])
+def test_prod_weighted_exchange_reproduces_oracle_chain(cuda, L, n_dim, alpha, std, total_sz, d_max, probs):
+    """ExchangeRule(probabilities=) (rules/exchange.py:86-123,155-182) on the product-form kernel: inverse-CDF cluster choice over
+    the hoppable clusters' weights and the weighted log_prob_corr.  probs=None: one random weight per cluster."""
+    nk = _nk()
+    B, CL = 24, 3
+    g = nk.graph.Hypercube(L, n_dim)
+    N = g.n_nodes
+    hi = nk.hilbert.Spin(0.5, N, total_sz=total_sz)
+    (W, b, a), var = _params(N, alpha, np.float64, std)
+    model = nk.models.RBM(alpha=alpha, param_dtype=np.float64)
+    e, col = ograph.hypercube_edges(L, n_dim)
+    clusters = ograph.compute_clusters(N, e, d_max)
+    if probs is None:
+        rule = nk.sampler.ExchangeRule(clusters=clusters, probabilities=np.random.default_rng(5).uniform(0.1, 2.0, len(clusters)))
+    else:
+        rule = nk.sampler.ExchangeRule(graph=g, d_max=d_max, probabilities=probs)
+    assert np.array_equal(clusters, rule.clusters)
+    sa = nk.sampler.MetropolisSampler(hi, rule, n_chains=B)
+    st = sa.init_state(model, var, seed=15324)
+    seed, t0 = st.rng
+    ref = osampler.sample_chain("exchange", st.σ.cpu().numpy(), W, b, a, chain_length=CL, seed=seed, t0=t0, clusters=clusters,
+                                probabilities=rule.probabilities)
+    for path in (PROD, 0):  # AUTO takes the same kernel
+        (samples, logp), st2 = sa.sample(model, var, state=st, chain_length=CL, return_log_probabilities=True, _path=path)
+        assert np.array_equal(samples.cpu().numpy(), ref["samples"])
+        np.testing.assert_allclose(logp.cpu().numpy(), ref["log_prob_samples"], rtol=1e-10, atol=1e-10)
+        assert np.array_equal(st2.n_accepted_proc.cpu().numpy(), ref["n_accepted"])
+    # the weights matter: the uniform rule draws different chains from the same stream
+    su, _ = nk.sampler.MetropolisExchange(hi, graph=g, d_max=d_max, n_chains=B).sample(model, var, state=st, chain_length=CL, _path=PROD)
+    assert not np.array_equal(su.cpu().numpy(), ref["samples"])
+    # fp32 follows the same chains except at accept-boundary ties; fused Heisenberg E_loc on the weighted chain
+    (W32, b32, a32), var32 = _params(N, alpha, np.float32, std)
+    model32 = nk.models.RBM(alpha=alpha, param_dtype=np.float32)
+    st32 = sa.init_state(model32, var32, seed=15324)
+    W64, b64, a64 = _f64(W32, b32, a32)
+    ref32 = osampler.sample_chain("exchange", st32.σ.cpu().numpy(), W64, b64, a64, chain_length=CL, seed=st32.rng[0], t0=st32.rng[1],
+                                  clusters=clusters, probabilities=rule.probabilities)
+    op = nk.operator.Heisenberg(hi, g)
+    samples32, _, eloc32, _ = sa._launch(model32, var32, st32, CL, operator=op, path=PROD)
+    same = np.all(samples32.cpu().numpy() == ref32["samples"], axis=(1, 2))
+    assert same.mean() >= 0.8, same.mean()
+    tables = oops.heisenberg_tables(e, col, J=1.0, sign_rule=ograph.is_bipartite(N, e))
+    refe = oest.local_estimators(samples32.cpu().numpy(), lambda x: oops.local_operator_conn_padded(x, tables), W64, b64, a64)
+    assert_rel(eloc32.cpu().numpy(), refe, F32_TOL_LARGE_W if std > 0.2 else F32_TOL)
+
+
 # ----------------------------------------------------------------------------------------- fp32 chains
 @pytest.mark.parametrize("rule,L,n_dim,alpha,std,total_sz,d_max", [
     ("local", 20, 1, 1, 0.3, None, 1), ("local", 10, 2, 4, 0.05, None, 1), ("exchange", 12, 1, 2, 0.5, 0, 2),
