@@ -234,7 +234,7 @@ static int prod_warps(int dtype, int rule) {
                          : (rule == NK_RULE_LOCAL ? ProdWarps<double, NK_RULE_LOCAL>::value : ProdWarps<double, NK_RULE_EXCHANGE>::value);
 }
 
-// M <= 512: one warp per chain.  Larger hidden layers (LocalRule): kw warps per chain, chosen to waste the least padding
+// M <= 512: one warp per chain.  Larger hidden layers: kw warps per chain, chosen to waste the least padding
 // among the instantiated segment shapes (at least half-full segments), then the fewest warps.
 #ifndef NK_PROD_MULTI_MAX_FULL_F32
 #define NK_PROD_MULTI_MAX_FULL_F32 5
@@ -245,7 +245,6 @@ static bool prod_shape(int M, int dtype, int rule, ProdShape *ps) {
     ps->mw = M;
     return true;
   }
-  if (rule != NK_RULE_LOCAL) return false;
   const int warps = prod_warps(dtype, rule);
   const int min_full = dtype == NK_F32 ? 2 : 4;
   long best = -1;
@@ -255,7 +254,7 @@ static bool prod_shape(int M, int dtype, int rule, ProdShape *ps) {
     // fp32 segments of up to 5 x 128 units (20 per lane) exist for the multi-warp kernel only: fewer, fatter warps per chain
     // mean more chains in flight per SM (M = 3200: 5 warps x 640 units, 4 chains per SM instead of 2)
     if (!seg_shape(mw, dtype, &c, NK_PROD_MULTI_MAX_FULL_F32) || c.nfull < min_full) continue;
-    if (c.nfull == 5 && c.tail != 0) continue;
+    if (dtype == NK_F32 && c.nfull >= 4 && c.tail != 0) continue;  // (4, 0) and (5, 0) are the instantiated fat segments
     const long cost = (long)kw * c.mp * 64 + kw;
     if (best < 0 || cost < best) {
       best = cost;
@@ -333,7 +332,7 @@ static bool prod_layout(const SweepKernelArgs &a, const ProdShape &ps, ProdLayou
     n_res = budget / L->row_bytes;
     if (n_res > N) n_res = N;
     if (esz == 4 && !multi && n_res < N) {
-      if (a.rule != NK_RULE_LOCAL || ps.nfull < 2) return false;
+      if (ps.nfull < 2) return false;
       multi = 1;
       continue;
     }
@@ -402,7 +401,9 @@ int sweep_prod(cudaStream_t stream, const SweepKernelArgs &a, const void *theta_
     NK_LAUNCH_OK();
     prod_prep_tables<float><<<1, 256, 0, stream>>>(pa, ps.ne_pad);
     NK_LAUNCH_OK();
-    if (multi) return launch_prod_f32_local_multi(stream, pa, ps.nfull, ps.tail);
+    if (multi)
+      return a.rule == NK_RULE_LOCAL ? launch_prod_f32_local_multi(stream, pa, ps.nfull, ps.tail)
+                                     : launch_prod_f32_exchange_multi(stream, pa, ps.nfull, ps.tail);
     return a.rule == NK_RULE_LOCAL ? launch_prod_f32_local(stream, pa, ps.nfull, ps.tail)
                                    : launch_prod_f32_exchange(stream, pa, ps.nfull, ps.tail);
   }
@@ -410,7 +411,9 @@ int sweep_prod(cudaStream_t stream, const SweepKernelArgs &a, const void *theta_
   NK_LAUNCH_OK();
   prod_prep_tables<double><<<1, 256, 0, stream>>>(pa, ps.ne_pad);
   NK_LAUNCH_OK();
-  if (multi) return launch_prod_f64_local_multi(stream, pa, ps.nfull, ps.tail);
+  if (multi)
+    return a.rule == NK_RULE_LOCAL ? launch_prod_f64_local_multi(stream, pa, ps.nfull, ps.tail)
+                                   : launch_prod_f64_exchange_multi(stream, pa, ps.nfull, ps.tail);
   if (run_if == nullptr && sweep_shadow_supported(a, pa.L)) {
     // fp32 shadow decisions + streamed double table (sweep_shadow.cu); if the weights are outside the shadow's range it raises
     // flags[8] and the one-table kernel, queued behind with that guard, does the work

@@ -1066,7 +1066,7 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
 #pragma unroll
               for (int q = 0; q < NV; ++q) c[q] = vfma(Bv[q], g[q], t[q]);
               const LanePair<T> P = lane_product1<V, NV>(c);
-              const int Rp = __reduce_add_sync(FULL, lp_fx(P, wide));
+              const int Rp = gcomb(__reduce_add_sync(FULL, lp_fx(P, wide)), op_add);
               const int X = (int)((uint32_t)Rp - (uint32_t)R + (uint32_t)cfix);
               bool acc;
               if constexpr (F64) {
@@ -1075,7 +1075,7 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
                 else if (thr >= X + PROD_FX_BAND)
                   acc = false;
                 else
-                  acc = exact_decide(exact_logratio(lp_val(P), lane_norm()), rp.xn + rp.yn + rm.xn - rm.yn, __shfl_sync(FULL, u_l, k), pw,
+                  acc = exact_decide(gcomb(exact_logratio(lp_val(P), lane_norm()), op_add), rp.xn + rp.yn + rm.xn - rm.yn, __shfl_sync(FULL, u_l, k), pw,
                                      cprob != nullptr ? corr_w : log((double)n_hop) - log((double)nhp));
               } else {
                 acc = thr < X;
@@ -1139,5 +1139,7 @@ int launch_prod_f64_exchange(cudaStream_t stream, const ProdArgs &a, int nfull, 
 // several warps per chain (M > 512): LocalRule only
 int launch_prod_f32_local_multi(cudaStream_t stream, const ProdArgs &a, int nfull, int tail);
 int launch_prod_f64_local_multi(cudaStream_t stream, const ProdArgs &a, int nfull, int tail);
+int launch_prod_f32_exchange_multi(cudaStream_t stream, const ProdArgs &a, int nfull, int tail);
+int launch_prod_f64_exchange_multi(cudaStream_t stream, const ProdArgs &a, int nfull, int tail);
 
 }  // namespace nk

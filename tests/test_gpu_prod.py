@@ -375,8 +375,12 @@ def test_prod_standalone_eloc_hands_over_for_large_weights(cuda):
 LARGE = [("local", 20, 1, 32, 0.01, None, 1),      # N=20, M=640: 2 warps per chain
          ("local", 16, 1, 100, 0.005, None, 1),    # N=16, M=1600: 4-5 warps per chain
          ("local", 12, 2, 4, 0.02, None, 1),       # N=144, M=576: 2 warps per chain, N > 128
+         ("local", 10, 1, 110, 0.01, None, 1),     # N=10, M=1100: two 550-unit segments would need an uninstantiated shape -> 3 warps
          ("local", 14, 2, 2, 0.03, None, 1),       # N=196, M=392: one warp per chain, table (326 KB fp32) not resident
-         ("exchange", 12, 2, 1, 0.05, 0, 1)]       # N=144 exchange, 288 clusters
+         ("exchange", 12, 2, 1, 0.05, 0, 1),       # N=144 exchange, 288 clusters
+         ("exchange", 20, 1, 32, 0.01, 0, 2),      # N=20, M=640 exchange: 2 warps per chain, every warp keeps the hoppable-cluster words
+         ("exchange", 6, 2, 32, 0.01, 0, 1),       # N=36, M=1152 exchange on a 2d lattice
+         ("exchange", 14, 2, 2, 0.03, 0, 1)]       # N=196, M=392 exchange: the fp32 table is not resident either (rows through L2)
 
 
 @pytest.mark.parametrize("rule,L,n_dim,alpha,std,total_sz,d_max", LARGE)
