@@ -51,7 +51,30 @@ __global__ void __launch_bounds__(256) ising_conn_kernel(const __grid_constant__
         reinterpret_cast<float *>(p.mels)[s * K + k] = (float)m;
     }
     // slots: row 0 = sigma, row k = sigma with site k-1 flipped (eye(N+1, N, k=-1), jax.py:158-160)
-    if (WORDS) {
+    if (WORDS && N <= 128) {
+      // rows of at most 32 words: lane l owns word column l of every row (no division; the rows of a sample are contiguous, so a
+      // warp store covers N contiguous bytes).  Row k flips site k - 1: the lane whose word holds it patches that byte, i.e.
+      // lane l patches rows 4l + 1 .. 4l + 4.  (The flat loop below spends ~13 instructions per stored word on index
+      // arithmetic and was issue-bound at 0.78 of the HBM write bandwidth: ncu, profiles/r02_k4_ising_conn_ncu_raw.csv.)
+      const uint32_t wpr = (uint32_t)N >> 2;
+      if ((uint32_t)lane < wpr) {
+        const uint32_t myw = reinterpret_cast<const uint32_t *>(sig)[lane];
+        uint32_t *out = reinterpret_cast<uint32_t *>(p.xp + (size_t)s * K * N) + lane;
+        const uint32_t first = 4u * (uint32_t)lane + 1u;  // first row this lane patches
+        int k = 0;
+        for (; k + 4 <= K; k += 4) {
+#pragma unroll
+          for (int d = 0; d < 4; ++d) {
+            const uint32_t off = (uint32_t)(k + d) - first;
+            out[(size_t)(k + d) * wpr] = off < 4u ? myw ^ (0xFEu << (off * 8u)) : myw;
+          }
+        }
+        for (; k < K; ++k) {
+          const uint32_t off = (uint32_t)k - first;
+          out[(size_t)k * wpr] = off < 4u ? myw ^ (0xFEu << (off * 8u)) : myw;
+        }
+      }
+    } else if (WORDS) {
       const uint32_t wpr = (uint32_t)N >> 2;
       const uint32_t total = (uint32_t)K * wpr;
       const uint32_t *sw = reinterpret_cast<const uint32_t *>(sig);
