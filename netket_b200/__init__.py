@@ -16,4 +16,9 @@ from . import convergence, driver, graph, hilbert, models, operator, optimizer, 
 from ._lib import NkError, LIB_PATH  # noqa: F401
 from .config import config  # noqa: F401
 
+# netket/stats/__init__.py:20 exports the estimator containers from `nk.stats` (they are defined next to the multimethods that
+# return them)
+stats.LocalEstimators = vqs.LocalEstimators
+stats.LocalEstimatorsBatch = vqs.LocalEstimatorsBatch
+
 __version__ = "0.1.0"

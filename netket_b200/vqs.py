@@ -42,18 +42,137 @@ def compute_chain_length(n_chains, n_samples):
     return chain_length
 
 
+# array attributes the reference forwards to ``.data`` for backward compatibility (local_estimators.py:37-44, 84-94); the
+# torch.Tensor spelling of the same names
+_ARRAY_LIKE_ATTRS = frozenset({"reshape", "mean", "std", "sum", "min", "max", "flatten", "ravel", "T", "dtype", "real", "imag",
+                               "conj", "tolist", "item", "size", "ndim", "shape", "cpu", "numpy", "device"})
+
+
 class LocalEstimators:
-    """netket/_src/stats/local_estimators.py:47-129 (``data`` (n_chains, chain_length), ``to_stats``)."""
+    """Per-sample scalar estimators, ``data`` of shape (n_chains, chain_length) (netket/_src/stats/local_estimators.py:47-129):
+    ``to_stats()`` one-shot ``Stats``; ``to_online_stats()`` / ``accumulate(old)`` start or update the streaming accumulator
+    (``OnlineStats``, K7).  Array attributes are forwarded to ``.data`` as the reference does."""
 
     def __init__(self, data):
         self.data = data
 
+    def __getattr__(self, name):
+        # the reference forwards a list of array attributes (and everything else works there through __jax_array__); a torch
+        # tensor's methods (.abs(), .to(), ...) are the counterpart of jnp functions applied to the container
+        if name != "data" and not name.startswith("_") and (name in _ARRAY_LIKE_ATTRS or hasattr(self.data, name)):
+            return getattr(self.data, name)
+        raise AttributeError(f"LocalEstimators has no attribute {name!r}.")
+
+    # the reference's container converts implicitly to an array (`__jax_array__`, local_estimators.py:75-83): the torch spelling
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        from torch.utils._pytree import tree_map
+
+        unwrap = lambda x: x.data if isinstance(x, LocalEstimators) else x  # noqa: E731
+        return func(*tree_map(unwrap, args), **tree_map(unwrap, kwargs or {}))
+
+    def __array__(self, dtype=None):
+        a = self.data.detach().cpu().numpy()
+        return a if dtype is None else a.astype(dtype)
+
+    def __len__(self):
+        return len(self.data)
+
+    def __getitem__(self, idx):
+        return self.data[idx]
+
+    def __neg__(self):
+        return -self.data
+
+    def __add__(self, o):
+        return self.data + getattr(o, "data", o)
+
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        return self.data - getattr(o, "data", o)
+
+    def __rsub__(self, o):
+        return getattr(o, "data", o) - self.data
+
+    def __mul__(self, o):
+        return self.data * getattr(o, "data", o)
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, o):
+        return self.data / getattr(o, "data", o)
+
+    def __pow__(self, o):
+        return self.data ** o
+
     def to_stats(self):
         return statistics(self.data)
 
+    def to_online_stats(self, *, max_lag=64):
+        from .stats import online_statistics
+
+        return online_statistics(self.data, None, max_lag=max_lag)
+
+    def accumulate(self, old=None, *, max_lag=64):
+        """Fold this batch into an online accumulator (``old`` from a previous call, or None to start one)."""
+        if old is None:
+            return self.to_online_stats(max_lag=max_lag)
+        return old.update(self.data)
+
+
+class LocalEstimatorsBatch:
+    """K-channel estimators for nonlinear observables, ``data`` of shape (n_chains, chain_length, K), with a ``combinator``
+    ``(K,) -> scalar | array`` of the channel means whose error is propagated by the delta method
+    (netket/_src/stats/local_estimators.py:132-246).  ``combinator`` is a function of a float64 torch vector."""
+
+    def __init__(self, data, combinator):
+        self.data = data
+        self.combinator = combinator
+
     @property
-    def shape(self):
-        return tuple(self.data.shape)
+    def n_channels(self):
+        return int(self.data.shape[-1])
+
+    def __getattr__(self, name):
+        if name in _ARRAY_LIKE_ATTRS:
+            raise AttributeError(f"LocalEstimatorsBatch has no attribute {name!r}. The underlying array is at .data; "
+                                 f"use le.data.{name} instead.")
+        raise AttributeError(f"LocalEstimatorsBatch has no attribute {name!r}.")
+
+    def to_stats(self):
+        """Delta-method statistics of this batch alone: covariance of the chain means (of the samples when there is one chain);
+        over all ranks.  ``Stats`` for a scalar combinator, ``StatsBatch`` for an array-valued one."""
+        import torch
+
+        from .stats import _allreduce, _delta_method_stats
+
+        d = self.data.to(torch.float64)
+        K = d.shape[-1]
+        rows = d.mean(dim=1) if d.shape[0] >= 1 else d.reshape(0, K)  # chain means of this rank
+        # first and second moments over ALL chains (one all-reduce of K + K^2 + 1 doubles), then the centred covariance
+        pack = torch.cat([rows.sum(dim=0), (rows.T @ rows).reshape(-1), torch.tensor([float(rows.shape[0])], dtype=torch.float64,
+                                                                                     device=d.device)])
+        pack = _allreduce(pack)
+        n = float(pack[-1].item())
+        X = pack[:K] / n
+        if n < 2:  # one chain in total: the samples themselves (local_estimators.py:206-210)
+            flat = d.reshape(-1, K)
+            dev = flat - X[None, :]
+            Cov = (dev.T @ dev) / float(flat.shape[0]) ** 2
+        else:
+            Cov = (pack[K:K + K * K].reshape(K, K) / n - X[:, None] * X[None, :]) / n
+        return _delta_method_stats(self.combinator, X, Cov)
+
+    def to_online_stats(self, *, max_lag=64):
+        from .stats import OnlineStatsBatch
+
+        return OnlineStatsBatch.from_data(self.data, self.combinator, max_lag=max_lag)
+
+    def accumulate(self, old=None, *, max_lag=64):
+        if old is None:
+            return self.to_online_stats(max_lag=max_lag)
+        return old.update(self.data)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -342,8 +461,9 @@ class MCState:
 
     def local_estimators(self, op, *, chunk_size=None):
         """O_loc for every sample, shape (n_chains_per_rank, chain_length) (state.py:612-692): the `local_estimators`
-        multimethod on (type(self), type(op), chunk_size), `.data` of its result."""
-        return local_estimators(self, op, self.chunk_size if chunk_size is None else chunk_size).data
+        multimethod on (type(self), type(op), chunk_size).  Returns the reference's container (`LocalEstimators`: `.data`,
+        `to_stats()`, `accumulate()`; usable wherever a tensor is, like the reference's implicit array conversion)."""
+        return local_estimators(self, op, self.chunk_size if chunk_size is None else chunk_size)
 
     def expect(self, op):
         """<O> with MC statistics (state.py:695-712): the `expect` multimethod.  For the built-in operators and no cached
@@ -422,7 +542,7 @@ class MCState:
             self._samples, eloc = self._run(self._chain_length, self._n_discard, operator=op, want_tanh=True, fused_stats=True)
             self._eloc_cache = (op, eloc)
         stats = self.expect(op)
-        eloc = self.local_estimators(op)
+        eloc = self.local_estimators(op).data
         samples = self.samples
         rbm = RBM.c_struct(self._variables)
         W, b, a = RBM.unpack(self._variables)

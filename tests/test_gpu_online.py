@@ -317,3 +317,58 @@ def test_online_stats_batch_delta_method(cuda):
     assert np.isnan(one.get_stats().error_of_mean)  # fewer than two chains: no covariance (accumulator_batch.py:199-200)
     with pytest.raises(ValueError, match="3D"):
         nk.stats.OnlineStatsBatch.from_data(torch.zeros((4, 4)).cuda(), f)
+
+
+def test_local_estimator_containers(cuda):
+    """LocalEstimators / LocalEstimatorsBatch (netket/_src/stats/local_estimators.py:47-246): `to_stats`, `to_online_stats`,
+    `accumulate`, attribute forwarding; the batch container's one-shot delta-method statistics against NumPy."""
+    import netket_b200 as nk
+
+    vs, H = small_state(nk, n_samples=64)
+    le = vs.local_estimators(H)
+    assert isinstance(le, nk.stats.LocalEstimators) and tuple(le.shape) == tuple(le.data.shape) and le.dtype == le.data.dtype
+    with pytest.raises(AttributeError, match="no attribute 'foo'"):
+        le.foo
+    st = le.to_stats()
+    np.testing.assert_allclose(st.mean, vs.expect(H).mean, rtol=1e-12)
+    acc = le.accumulate(max_lag=4)
+    assert isinstance(acc, nk.stats.OnlineStats)
+    np.testing.assert_allclose(acc.mean, st.mean, rtol=1e-10)
+    vs.sample(n_discard_per_chain=0)
+    le2 = vs.local_estimators(H)
+    acc2 = le2.accumulate(acc)
+    both = torch.cat([le.data, le2.data], dim=1)
+    np.testing.assert_allclose(acc2.mean, both.mean().item(), rtol=1e-10)
+    assert acc2.n_samples == both.numel()
+    # K channels: the variance observable  <E^2> - <E>^2  and an array-valued combinator
+    e = le.data.to(torch.float64)
+    comb = lambda mu: mu[1] - mu[0] ** 2  # noqa: E731
+    leb = nk.stats.LocalEstimatorsBatch(torch.stack([e, e * e], dim=-1), comb)
+    assert leb.n_channels == 2
+    with pytest.raises(AttributeError, match="use le.data.mean"):
+        leb.mean
+    x = leb.data.cpu().numpy()
+    cm = x.mean(axis=1)
+    X = cm.mean(axis=0)
+    D = (cm - X).T
+    Cov = D @ D.T / cm.shape[0] ** 2
+    J = np.array([-2.0 * X[0], 1.0])
+    sb = leb.to_stats()
+    np.testing.assert_allclose(sb.mean, X[1] - X[0] ** 2, rtol=1e-11)
+    np.testing.assert_allclose(sb.error_of_mean, np.sqrt(J @ Cov @ J), rtol=1e-8)
+    accb = leb.accumulate(max_lag=4)
+    assert isinstance(accb, nk.stats.OnlineStatsBatch)
+    np.testing.assert_allclose(accb.get_stats().mean, sb.mean, rtol=1e-10)
+    np.testing.assert_allclose(accb.get_stats().error_of_mean, sb.error_of_mean, rtol=1e-8)
+    e2 = le2.data.to(torch.float64)
+    accb2 = nk.stats.LocalEstimatorsBatch(torch.stack([e2, e2 * e2], dim=-1), comb).accumulate(accb)
+    assert accb2.n_samples == 2 * e.numel()
+    arr = nk.stats.LocalEstimatorsBatch(leb.data, lambda mu: torch.stack([mu[0], mu[1] - mu[0] ** 2])).to_stats()
+    assert arr.shape == (2,)
+    np.testing.assert_allclose(arr.mean.cpu().numpy(), [X[0], X[1] - X[0] ** 2], rtol=1e-11)
+    one = nk.stats.LocalEstimatorsBatch(leb.data[:1], comb).to_stats()  # a single chain: covariance of the samples
+    flat = x[:1].reshape(-1, 2)
+    X1 = flat.mean(axis=0)
+    C1 = (flat - X1).T @ (flat - X1) / flat.shape[0] ** 2
+    J1 = np.array([-2.0 * X1[0], 1.0])
+    np.testing.assert_allclose(one.error_of_mean, np.sqrt(J1 @ C1 @ J1), rtol=1e-8)

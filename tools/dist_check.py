@@ -20,7 +20,7 @@ for dtype in (np.float64, np.float32):
         pass
     # gather samples / eloc to rank 0 and recompute there with the oracle
     samples = [torch.empty_like(vs.samples) for _ in range(ws)]; dist.all_gather(samples, vs.samples)
-    eloc = [torch.empty_like(vs.local_estimators(op)) for _ in range(ws)]; dist.all_gather(eloc, vs.local_estimators(op))
+    eloc = [torch.empty_like(vs.local_estimators(op).data) for _ in range(ws)]; dist.all_gather(eloc, vs.local_estimators(op).data)
     if rank == 0:
         from oracle import forces as oforces, stats as ostats
         S = torch.cat(samples).cpu().numpy(); E = torch.cat(eloc).cpu().numpy()
