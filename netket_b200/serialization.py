@@ -115,3 +115,86 @@ def deserialize_MCState(vstate, state_dict):
     new.n_discard_per_chain = state_dict["n_discard_per_chain"]
     new.chunk_size = state_dict["chunk_size"]
     return new
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Bytes: the msgpack wire format of `flax.serialization.to_bytes / from_bytes` (what NetKet users write to `.mpack` files:
+# docs `flax.serialization.to_bytes(vstate)`).  flax (>= 0.10.6, pyproject.toml:44) is a third-party dependency that is neither in
+# /root/reference nor in this image, so its published format is RESTATED here and is unverified against flax itself ("parity
+# unpinned" for this format; the round trip and a hand-assembled byte string are what tests/test_host_logic.py and tests/test_gpu_serialization.py check):
+#   * the state dict is packed with msgpack (`strict_types=True`), dict keys are strings;
+#   * an ndarray is ExtType(1, packb((shape, dtype.name, C-order bytes), use_bin_type=True));
+#   * a Python complex is ExtType(2, packb((re, im))); a NumPy scalar is ExtType(3, <the ndarray encoding of asarray(x)>).
+# Arrays above 2^30 bytes are chunked by flax; this path never writes one (parameters and one rank-gathered sigma).
+# ------------------------------------------------------------------------------------------------------------------
+_EXT_NDARRAY, _EXT_COMPLEX, _EXT_NPSCALAR = 1, 2, 3
+_MAX_CHUNK = 2 ** 30
+
+
+def _ndarray_to_bytes(arr):
+    import msgpack
+
+    arr = np.asarray(arr)  # (tobytes("C") below linearises any layout; ascontiguousarray would turn a 0-d scalar into shape (1,))
+    if arr.dtype.hasobject:
+        raise ValueError("object arrays cannot be serialised")
+    if arr.nbytes > _MAX_CHUNK:
+        raise ValueError("arrays above 2^30 bytes are not written by this path (flax would chunk them)")
+    return msgpack.packb((arr.shape, arr.dtype.name, arr.tobytes("C")), use_bin_type=True)
+
+
+def _ndarray_from_bytes(data):
+    import msgpack
+
+    shape, dtype_name, buf = msgpack.unpackb(data, raw=True)
+    return np.frombuffer(buf, dtype=np.dtype(dtype_name.decode()), count=-1, offset=0).reshape(shape, order="C").copy()
+
+
+def _ext_pack(x):
+    import msgpack
+
+    if isinstance(x, torch.Tensor):
+        x = _np(x)
+    if isinstance(x, np.ndarray):
+        return msgpack.ExtType(_EXT_NDARRAY, _ndarray_to_bytes(x))
+    if isinstance(x, np.generic):
+        return msgpack.ExtType(_EXT_NPSCALAR, _ndarray_to_bytes(np.asarray(x)))
+    if isinstance(x, complex):
+        return msgpack.ExtType(_EXT_COMPLEX, msgpack.packb((x.real, x.imag)))
+    return x
+
+
+def _ext_unpack(code, data):
+    import msgpack
+
+    if code == _EXT_NDARRAY:
+        return _ndarray_from_bytes(data)
+    if code == _EXT_NPSCALAR:
+        return _ndarray_from_bytes(data)[()]
+    if code == _EXT_COMPLEX:
+        re, im = msgpack.unpackb(data)
+        return complex(re, im)
+    return msgpack.ExtType(code, data)
+
+
+def msgpack_serialize(state_dict):
+    """``flax.serialization.msgpack_serialize``: nested dict of arrays / scalars -> bytes."""
+    import msgpack
+
+    return msgpack.packb(state_dict, default=_ext_pack, strict_types=True)
+
+
+def msgpack_restore(data):
+    """``flax.serialization.msgpack_restore``: bytes -> nested dict of NumPy arrays / scalars."""
+    import msgpack
+
+    return msgpack.unpackb(data, ext_hook=_ext_unpack, raw=False)
+
+
+def to_bytes(vstate):
+    """``flax.serialization.to_bytes(vstate)``: the msgpack of ``serialize_MCState(vstate)``."""
+    return msgpack_serialize(serialize_MCState(vstate))
+
+
+def from_bytes(vstate, data):
+    """``flax.serialization.from_bytes(vstate, data)``: a copy of ``vstate`` restored from the bytes."""
+    return deserialize_MCState(vstate, msgpack_restore(data))

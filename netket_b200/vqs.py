@@ -588,6 +588,18 @@ class MCState:
 
         return deserialize_MCState(self, state_dict)
 
+    def to_bytes(self):
+        """``flax.serialization.to_bytes(vstate)``: msgpack bytes in flax's wire format (serialization.py)."""
+        from .serialization import to_bytes
+
+        return to_bytes(self)
+
+    def from_bytes(self, data):
+        """``flax.serialization.from_bytes(vstate, data)``: a copy of this state restored from the bytes."""
+        from .serialization import from_bytes
+
+        return from_bytes(self, data)
+
     def __repr__(self):
         return (f"MCState(\n  hilbert = {self.hilbert},\n  sampler = {self._sampler},\n  n_samples = {self.n_samples},\n"
                 f"  n_discard_per_chain = {self._n_discard},\n  sampler_state = {self.sampler_state},\n"

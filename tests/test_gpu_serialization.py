@@ -46,6 +46,12 @@ def test_mcstate_round_trip_resumes_the_same_chains(cuda):
     sd2 = vs.to_state_dict()
     again = other.from_state_dict(sd2)
     assert torch.equal(again.samples, s1)
+    # the msgpack bytes of flax.serialization.to_bytes / from_bytes (wire format restated in serialization.py)
+    blob = vs.to_bytes()
+    assert isinstance(blob, bytes)
+    from_blob = other.from_bytes(blob)
+    assert torch.equal(from_blob.samples, s1) and from_blob.n_samples == vs.n_samples
+    assert torch.equal(from_blob.parameters["Dense"]["kernel"], vs.parameters["Dense"]["kernel"])
     # and both continue identically
     vs.reset()
     restored.reset()

@@ -177,3 +177,34 @@ def test_no_cpu_fallback_for_numerics():
         nk.operator.Ising(hi, nk.graph.Chain(4), h=1.0).get_conn_padded(np.ones((2, 4)))
     with pytest.raises(nk.NkError):
         nk.stats.statistics(np.zeros((4, 4)))
+
+
+def test_msgpack_wire_format_of_state_dicts():
+    """The bytes of `flax.serialization.to_bytes` as restated in netket_b200/serialization.py: a hand-assembled byte string in
+    that format (ExtType 1 = packb((shape, dtype name, C bytes)), ExtType 3 for NumPy scalars, ExtType 2 for complex) decodes to the
+    expected tree, and a tree of arrays / scalars / None round-trips bit for bit."""
+    import msgpack
+
+    from netket_b200 import serialization as ser
+
+    a = np.arange(6, dtype=np.float32).reshape(2, 3)
+    ext_a = msgpack.ExtType(1, msgpack.packb(((2, 3), "float32", a.tobytes()), use_bin_type=True))
+    ext_s = msgpack.ExtType(3, msgpack.packb(((), "int64", np.int64(7).tobytes()), use_bin_type=True))
+    ext_c = msgpack.ExtType(2, msgpack.packb((1.5, -2.0)))
+    blob = msgpack.packb({"variables": {"params": {"Dense": {"kernel": ext_a}}}, "n_samples": 1008, "k": ext_s, "z": ext_c, "chunk_size": None})
+    tree = ser.msgpack_restore(blob)
+    assert np.array_equal(tree["variables"]["params"]["Dense"]["kernel"], a) and tree["variables"]["params"]["Dense"]["kernel"].dtype == np.float32
+    assert tree["n_samples"] == 1008 and tree["k"] == 7 and isinstance(tree["k"], np.int64) and tree["z"] == complex(1.5, -2.0)
+    assert tree["chunk_size"] is None
+    # our writer produces exactly those bytes for the same tree
+    same = ser.msgpack_serialize({"variables": {"params": {"Dense": {"kernel": a}}}, "n_samples": 1008, "k": np.int64(7), "z": complex(1.5, -2.0),
+                                  "chunk_size": None})
+    assert same == blob
+    big = {"sampler_state": {"σ": np.random.default_rng(0).choice([-1, 1], size=(5, 7)).astype(np.int8), "rng": np.array([3, 9], dtype=np.uint64),
+                             "n_accepted_proc": np.arange(5, dtype=np.int64)}, "w": np.random.default_rng(1).normal(size=(3, 4))}
+    back = ser.msgpack_restore(ser.msgpack_serialize(big))
+    for k, v in big["sampler_state"].items():
+        assert np.array_equal(back["sampler_state"][k], v) and back["sampler_state"][k].dtype == v.dtype
+    assert np.array_equal(back["w"], big["w"])
+    with pytest.raises(ValueError, match="object arrays"):
+        ser.msgpack_serialize({"x": np.array([object()])})
