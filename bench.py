@@ -306,10 +306,13 @@ def measure_e2e(nk, torch, dist, rank, ws, device, dtype, steps, warmup, params)
     d.return_samples = 1  # the samples are written to HBM as in the `value` path (and stay there, as MCState.samples do)
     d.ising_host = C.pointer(op)
     d.seed, d.chain_offset = SAMPLER_SEED, rank * CHAINS_PER_GPU
-    d.stream = torch.cuda.current_stream(device).cuda_stream  # torch.distributed orders its all-reduce after this stream
+    d.stream = None  # a stream of the context's own; the all-reduce below is issued on it (nk_ctx_stream)
     d.eloc_in_param_dtype = 1
     _lib.check(L.nk_ctx_create2(C.byref(ctx), C.byref(d)))
     part = torch.as_tensor(_DevPtr(L.nk_ctx_partials_device(ctx), _lib.NK_CTX_NPARTIAL), device=device)
+    # the context's stream as a torch stream: torch.distributed orders a collective after the work already queued on the CURRENT
+    # stream and makes that stream wait for it - so the all-reduce must be issued with the context's stream current
+    ctx_stream = torch.cuda.ExternalStream(int(L.nk_ctx_stream(ctx)), device=device)
     pin = lambda x: torch.from_numpy(x).pin_memory()  # noqa: E731
     Wp, bp, ap = pin(W), pin(b), pin(a)
     eloc = torch.empty((CHAINS_PER_GPU, CHAIN_LENGTH), dtype=Wp.dtype).pin_memory()
@@ -318,7 +321,8 @@ def measure_e2e(nk, torch, dist, rank, ws, device, dtype, steps, warmup, params)
     def step(n_discard=0):
         _lib.check(L.nk_ctx_step_begin(ctx, Wp.data_ptr(), bp.data_ptr(), ap.data_ptr(), n_discard))
         if ws > 1:
-            dist.all_reduce(part)  # NK_CTX_NPARTIAL doubles: the only cross-device traffic of a step
+            with torch.cuda.stream(ctx_stream):
+                dist.all_reduce(part)  # NK_CTX_NPARTIAL doubles: the only cross-device traffic of a step
         rc = L.nk_ctx_step_end(ctx, eloc.data_ptr(), None, stats)
         if rc not in (0, _lib.NK_RESHIFT):
             _lib.check(rc)

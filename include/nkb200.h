@@ -305,7 +305,9 @@ typedef struct nk_ctx_desc_t {
   const nk_ising_t *ising_host;     /* exactly one of the two operators; every pointer inside is a HOST pointer */
   const nk_localop_t *localop_host;
   uint64_t seed, chain_offset;
-  void *stream;                     /* cudaStream_t the context enqueues on, or NULL: a stream of its own */
+  void *stream;                     /* cudaStream_t the context enqueues on, or NULL: a (non-blocking) stream of its own.  NULL is NOT
+                                       the legacy default stream: pass cudaStreamLegacy ((cudaStream_t)0x1) to run on that one.  A
+                                       collective between step_begin and step_end must be ordered after / before nk_ctx_stream(ctx) */
   int32_t eloc_in_param_dtype;      /* 0: E_loc in promote(operator, parameter) = float64; 1: in the parameter dtype */
   int32_t reserved;
 } nk_ctx_desc_t;
