@@ -6,18 +6,20 @@
 //   S  sweep.  The accept / reject decisions are taken on an fp32 shadow of the state, (A32, B32) ~ (A, B), against an
 //      fp32 copy of the table G32 = float(exp(-4 W)) that IS resident (166 KB): exactly the proposal loop of sweep_fast.cu.
 //      A decision whose fixed-point margin |fix(log2 ratio) - fix(log2(u) / machine_pow)| lies within BAND of zero - the
-//      shadow's error is ~2 units typical, < 40 worst case - is re-decided in double precision from scratch
-//      (theta = sigma W + b, lncosh differences: the reference's arithmetic; ~4e-4 of the proposals).  So the chain is the
-//      fp64 chain, bit for bit, and no double is touched while sweeping.
+//      shadow's error is ~2 units typical, < 40 worst case - is re-decided in double precision, out of line (exact_accept:
+//      the parked double state brought up to date with the rows of the sites flipped since, the proposal's product formed in
+//      double, u < exp(machine_pow (x_i +- y_i + sum log(P / norm))): metropolis.py:441-450; ~1.6e-4 of the proposals at the
+//      benchmark's weights).  So the chain is the fp64 chain, bit for bit, and no double is touched while sweeping.
 //   U  update, once per sweep.  The double state only has to follow the NET change of the sweep: a site flipped an even number
 //      of times multiplies A_j and B_j by the same G_ij, which cancels in every ratio.  The double table is streamed once
-//      through a shared-memory ring by TMA bulk copies of 4 rows (one producer thread, full / empty mbarriers) and every warp applies the
-//      rows of its chain's net-flipped sites (~43 of 100) to its (A, B) registers; the state is rescaled by exact powers
-//      of two and the shadow is refreshed from it (its rounding drift never outlives a sweep).
+//      through a shared-memory ring by TMA bulk copies of 4 rows (warp 0 is a dedicated producer; full / empty mbarriers) and
+//      every consumer warp applies the rows of its chain's net-flipped sites (~43 of 100) to its (A, B) registers; the state is
+//      rescaled by exact powers of two and the shadow is refreshed from it (its rounding drift never outlives a sweep).
 //   E  local energy of a recorded sample: the table is streamed a second time, every warp forms prod_j (X_j G_ij + Y_j) for
 //      every site i in double (13 DFMA + 12 DMUL per lane), 8 sites per transposed multiplicative butterfly.
-// L2 -> shared traffic is one table per CTA and pass instead of one row per proposal and chain; the binding resource of U + E
-// is the shared-memory read of the streamed rows (143 double rows per sample and chain), of S the fp32 rows.
+// L2 -> shared traffic is one table per CTA and pass instead of one row per proposal and chain.  What binds the kernel is neither
+// a pipe nor a bandwidth but dependent-issue latency at 3 warps per scheduler (168 registers: 26 doubles of state per lane, two
+// rows in flight); measurements, per-phase cycle counts and the rejected variants: profiles/r02_shadow_f64_experiments.md.
 //
 // Replaces netket/sampler/metropolis.py:427-462 + rules/local.py:40-49, vqs/mc/kernels.py:62-71 with
 // operator/_ising/jax.py:125-165 and the sums of stats/mc_stats_old.py:87-196, like sweep_fast.cu / sweep_prod.cuh.
