@@ -720,17 +720,22 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_shadow_kernel(const __grid_c
             P = lane_product<NP2, NPA, HAS_T>(c.A2, c.At, c.B2, c.Bt, g2, gt);  // spin up (nu = -1): prod (A g + B)
           const int Rp = __reduce_add_sync(FULL, __float2int_rn(lg2_fast(P) * FX_SCALE));
           const int margin = (int)((uint32_t)Rp - (uint32_t)c.R + (sdown ? rec.w : 0u - rec.w) - rec.z);  // > 0 <=> accept
-          bool acc = margin > 0;
-          if (margin <= BAND && margin >= -BAND) {
-            // inside the shadow's error band: leave the loop, decide in double precision (a function call: kept out of the
-            // hot loop, whose registers it would otherwise push to the stack), come back to this proposal with the verdict
-            if (forced == 0) {
-              need_exact = true;
-              break;
+          // the common case first (~96 % of the proposals are accepted well clear of the band): one compare and branch.
+          // Inside the shadow's error band: leave the loop, decide in double precision (a function call: kept out of the hot
+          // loop, whose registers it would otherwise push to the stack), come back to this proposal with the verdict
+          bool acc = true;
+          if (margin <= BAND) {
+            if (margin < -BAND) {
+              acc = false;
+            } else {
+              if (forced == 0) {
+                need_exact = true;
+                break;
+              }
+              acc = forced == 2;
+              forced = 0;
             }
-            acc = forced == 2;
           }
-          forced = 0;
           if (acc) {
             if (sdown) {
 #pragma unroll
