@@ -92,10 +92,13 @@ __device__ __forceinline__ uint32_t sw4sel4(const uint32_t (&w)[4], int i) {
 // all lanes poll, the exit is a warp vote: the loop is uniform for the compiler (no divergence to repair around the warp-wide
 // reductions of the hot loops).  A poll is ~8 issued instructions; un-throttled, the polls of the producer (idle while the
 // consumers sweep) and of consumers waiting for the stream were 29 % of all instructions the kernel issued (ncu source page,
-// profiles/r02_shadow_polling.md), taken from the issue slots of the warps doing arithmetic: after FAST failed probes the
-// warp sleeps NS nanoseconds between probes.
+// profiles/r02_shadow_f64_experiments.md), taken from the issue slots of the warps doing arithmetic: after FAST failed probes
+// a consumer warp sleeps NS nanoseconds between probes (measured: no change in time either way).
 #ifndef NK_SH_PSLEEP
-#define NK_SH_PSLEEP 200
+#define NK_SH_PSLEEP 0  // the producer polls un-throttled: a sleeping producer issues the next copy late (U ring wait 6.5k -> 5.9k cycles)
+#endif
+#ifndef NK_SH_PFAST
+#define NK_SH_PFAST 4
 #endif
 #ifndef NK_SH_CSLEEP
 #define NK_SH_CSLEEP 40
@@ -337,7 +340,7 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_shadow_kernel(const __grid_c
     int gi = rotg;
     uint32_t st = 0, par = 0;  // parity of the `empty` phase to wait for (the stage's previous use); first waited at t = STAGES
     for (uint32_t t = 0; t < total_q; ++t) {
-      if (t >= (uint32_t)STAGES) mbar_wait_uniform<4, NK_SH_PSLEEP>(empty + st, par);
+      if (t >= (uint32_t)STAGES) mbar_wait_uniform<NK_SH_PFAST, NK_SH_PSLEEP>(empty + st, par);
       if (lane == 0) {
         const uint32_t bytes = (uint32_t)(min(GROUP, N - GROUP * gi) * row64);
         mbar_expect_tx(full + st, bytes);
