@@ -124,8 +124,47 @@ def edges_np():
     return ograph.hypercube_edges(L_SIDE, 2)[0]
 
 
+def run_netket_cpu(dtype, steps, warmup):
+    """NetKet itself on jax[cpu] (tried first).  Raises ImportError where jax / netket cannot be imported - which is
+    every box of this image: jax is not installed and `pip install --no-index` of the reference fails on it - and run_cpu then
+    times the port of the reference algorithm instead."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(ref) and ref not in sys.path:
+        sys.path.insert(0, ref)
+    os.environ.setdefault("JAX_PLATFORMS", "cpu")
+    import jax  # noqa: F401  (ImportError here is the expected outcome)
+    import netket as rnk
+
+    g = rnk.graph.Hypercube(length=L_SIDE, n_dim=2, pbc=True)
+    hi = rnk.hilbert.Spin(s=0.5, N=g.n_nodes)
+    ha = rnk.operator.Ising(hi, g, h=H_FIELD, J=J_COUP)
+    vs = rnk.vqs.MCState(rnk.sampler.MetropolisLocal(hi, n_chains=CPU_SAMPLE_CHAINS), rnk.models.RBM(alpha=ALPHA, param_dtype=np.dtype(dtype).type),
+                         n_samples=CPU_SAMPLE_CHAINS, n_discard_per_chain=0, seed=WEIGHT_SEED, sampler_seed=SAMPLER_SEED)
+
+    def step():
+        vs.reset()
+        le = vs.local_estimators(ha)
+        jax.block_until_ready(getattr(le, "data", le))
+
+    for _ in range(warmup + 1):  # + 1: compilation
+        step()
+    tic = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - tic
+    val = CPU_SAMPLE_CHAINS * steps / dt
+    return val, dt / steps * 1e3, {"value": val, "unit": "samples/s", "cores": os.cpu_count(), "kind": "reference",
+                                   "sample": f"{CPU_SAMPLE_CHAINS} chains x 1 (sweep + E_loc) per step, {steps} timed steps",
+                                   "what": "NetKet on jax[cpu]: vs.reset(); vs.local_estimators(H)"}
+
+
 def run_cpu(dtype, steps, warmup):
-    """The reference algorithm on the host cores, on a bounded sample of the workload (see cpu_baseline.sample)."""
+    """The reference on the host cores, on a bounded sample of the workload (see cpu_baseline.sample): NetKet itself where it can be
+    imported, else the port of its algorithm."""
+    try:
+        return run_netket_cpu(dtype, steps, warmup)
+    except Exception:  # ImportError (no jax) in this image; anything else: the port is always there
+        pass
     from oracle import reference_algorithm as ra
 
     # all the host threads the box has (torchrun exports OMP_NUM_THREADS=1, which would otherwise cap the baseline at one core)
