@@ -161,10 +161,11 @@ def run_netket_cpu(dtype, steps, warmup):
 def run_cpu(dtype, steps, warmup):
     """The reference on the host cores, on a bounded sample of the workload (see cpu_baseline.sample): NetKet itself where it can be
     imported, else the port of its algorithm."""
+    why = ""
     try:
         return run_netket_cpu(dtype, steps, warmup)
-    except Exception:  # ImportError (no jax) in this image; anything else: the port is always there
-        pass
+    except Exception as exc:  # ImportError (no jax) in this image; anything else: the port is always there
+        why = f"{type(exc).__name__}: {str(exc).splitlines()[0] if str(exc) else ''}"[:160]
     from oracle import reference_algorithm as ra
 
     # all the host threads the box has (torchrun exports OMP_NUM_THREADS=1, which would otherwise cap the baseline at one core)
@@ -175,7 +176,8 @@ def run_cpu(dtype, steps, warmup):
               "of chains once the GEMMs saturate the cores")
     return val, ms, {"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample,
                      "what": "reference algorithm (full forward pass per proposal, materialised connected states), torch CPU "
-                             "kernels on all host threads; NetKet's jax[cpu] path itself cannot run: jax is not installed"}
+                             "kernels on all host threads; NetKet's jax[cpu] path itself was tried first and cannot run here ("
+                             + why + ")"}
 
 
 def main_reference(args):
