@@ -52,14 +52,18 @@ static bool tc_geometry(const nk_rbm_t &rbm, TcGeom *g) {
 
 // ---------------------------------------------------------------------------------------------- prep: W -> 3 bf16 images
 // image[tile][part][(n / 8) * sbo + (k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2],  n = column inside the tile, k = site
-__global__ void theta_prep_kernel(const float *__restrict__ W, int N, int M, int kpad, int nt, int NT, int sbo, uint16_t *__restrict__ img) {
+// `bias` != nullptr (only when kpad > N): row k = N of the image holds the bias, multiplied by a column of ones in the A tile, so
+// that theta = sigma W + b comes out of the MMAs and the epilogue does no bias loads (they were ~45 % of its stall samples)
+__global__ void theta_prep_kernel(const float *__restrict__ W, const float *__restrict__ bias, int N, int M, int kpad, int nt, int NT, int sbo,
+                                  uint16_t *__restrict__ img) {
   const int total = nt * NT * kpad;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int k = idx % kpad;
     const int ncol = (idx / kpad) % NT;
     const int tile = idx / (kpad * NT);
     const int j = tile * NT + ncol;
-    const float w = (k < N && j < M) ? W[(size_t)k * M + j] : 0.0f;
+    float w = (k < N && j < M) ? W[(size_t)k * M + j] : 0.0f;
+    if (bias != nullptr && k == N && j < M) w = bias[j];
     const uint16_t h1 = f32_to_bf16_rn(w);
     const float r1 = w - bf16_to_f32(h1);
     const uint16_t h2 = f32_to_bf16_rn(r1);
@@ -82,6 +86,7 @@ struct TcArgs {
   float *theta;
   int64_t B;
   int N, M, kpad, nt, NT, sbo, tmem_cols, acc_cols, vec_ok;
+  int ones_col;  // 1: A carries a column of ones at k = N (the bias sits in the W image), `bias` is NULL
   uint32_t part_bytes, img_bytes;
 };
 
@@ -133,15 +138,33 @@ __global__ void __launch_bounds__(128, 1) theta_tc_kernel(const __grid_constant_
     const int64_t row = rb * 128 + tid;
     const int8_t *src = p.sigma + row * p.N;
     unsigned char *dst = a_tiles + buf * a_bytes + (size_t)(tid >> 3) * p.sbo + (size_t)(tid & 7) * 16;
+    // rows of whole, aligned 32-bit words (row * N is then a multiple of 4): 4 spins per load
+    const bool words = (p.N & 3) == 0 && (reinterpret_cast<uintptr_t>(p.sigma) & 3) == 0;
     for (int c = 0; c < p.kpad / 8; ++c) {
       uint32_t w[4] = {0u, 0u, 0u, 0u};
       if (row < p.B) {
+        if (words) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int k = 8 * c + e;
-          const uint32_t h = (k < p.N) ? (src[k] < 0 ? 0xBF80u : 0x3F80u) : 0u;
-          w[e >> 1] |= h << (16 * (e & 1));
+          for (int hw = 0; hw < 2; ++hw) {
+            const int k0 = 8 * c + 4 * hw;
+            if (k0 < p.N) {
+              const uint32_t v = *reinterpret_cast<const uint32_t *>(src + k0);  // bytes +1 = 0x01, -1 = 0xFF: bit 7 is the sign
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const uint32_t h = ((v >> (8 * e + 7)) & 1u) ? 0xBF80u : 0x3F80u;
+                w[2 * hw + (e >> 1)] |= h << (16 * (e & 1));
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int k = 8 * c + e;
+            const uint32_t h = (k < p.N) ? (src[k] < 0 ? 0xBF80u : 0x3F80u) : 0u;
+            w[e >> 1] |= h << (16 * (e & 1));
+          }
         }
+        if (p.ones_col && (p.N >> 3) == c) w[(p.N & 7) >> 1] |= 0x3F80u << (16 * (p.N & 1));  // 1.0 at k = N
       }
       *reinterpret_cast<uint4 *>(dst + (size_t)c * 128) = make_uint4(w[0], w[1], w[2], w[3]);
     }
@@ -274,16 +297,19 @@ int theta_gemm(cudaStream_t stream, const nk_rbm_t &rbm, const int8_t *sigma, in
   if (theta_dmma_supported(rbm)) return theta_dmma(stream, rbm, sigma, B, theta_out);  // fp64: DMMA
   if (!tc_geometry(rbm, &g)) return rbm_logpsi(stream, rbm, sigma, B, workspace, theta_out);
   uint16_t *img = reinterpret_cast<uint16_t *>(workspace);
+  const bool fold_bias = rbm.b != nullptr && g.kpad > rbm.N;  // a spare K slot: the bias rides along as row N of W
   {
     const int total = g.nt * g.NT * g.kpad;
-    theta_prep_kernel<<<(total + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const float *>(rbm.W), rbm.N, rbm.M, g.kpad, g.nt, g.NT,
-                                                               g.sbo, img);
+    theta_prep_kernel<<<(total + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const float *>(rbm.W),
+                                                               fold_bias ? reinterpret_cast<const float *>(rbm.b) : nullptr, rbm.N, rbm.M,
+                                                               g.kpad, g.nt, g.NT, g.sbo, img);
     NK_LAUNCH_OK();
   }
   TcArgs a{};
   a.sigma = sigma;
   a.img = img;
-  a.bias = reinterpret_cast<const float *>(rbm.b);
+  a.bias = fold_bias ? nullptr : reinterpret_cast<const float *>(rbm.b);
+  a.ones_col = fold_bias ? 1 : 0;
   a.theta = reinterpret_cast<float *>(theta_out);
   a.B = B;
   a.N = rbm.N;
