@@ -36,6 +36,10 @@ struct FtcArgs {
 };
 
 constexpr int FT_THREADS = 512;  // 16 warps: one group of 8 samples each per block (more theta loads in flight)
+#ifndef NK_FT_JB
+#define NK_FT_JB 4
+#endif
+constexpr int FT_JB = NK_FT_JB;  // row iterations of the B' fill whose loads are issued together
 
 __global__ void __launch_bounds__(FT_THREADS, 1) forces_tc_kernel(const __grid_constant__ FtcArgs p) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -68,6 +72,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) forces_tc_kernel(const __grid_c
   // rows (sites for A', hidden units for B').  Global reads are coalesced along the row index (theta[s, j0 + lane + 32 c],
   // sigma[s, lane + 32 c]) and every (row, 8 samples) chunk is written with one 128-bit shared-memory store per bf16 part.
   const int lane = tid & 31;
+  const bool sig_words = (p.N & 3) == 0 && (reinterpret_cast<uintptr_t>(p.sigma) & 3) == 0;
   uint32_t mma_phase = 0;
   int n_done = 0;
   for (int64_t blk = blockIdx.x / p.nt; blk < n_blocks; blk += ctas_per_tile, ++n_done) {
@@ -88,49 +93,88 @@ __global__ void __launch_bounds__(FT_THREADS, 1) forces_tc_kernel(const __grid_c
 #pragma unroll
       for (int q = 0; q < 8; ++q) w[q] = __shfl_sync(0xffffffffu, wl, q);
       // ---- A'[i, s] = sigma[s, i] (+1 = 0x3F80, -1 = 0xBF80), row N = ones
-      for (int i = lane; i < 128; i += 32) {
-        uint32_t pk[4] = {0u, 0u, 0u, 0u};
+      if (sig_words) {
+        // rows of whole, aligned 32-bit words: lane l reads sites 4l .. 4l+3 of the 8 samples with 8 loads (bit 7 of a byte is
+        // the sign) and writes the four rows' chunks; the ones row N and the zero rows above it are written by the next lanes
+        uint32_t v[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          uint32_t h = 0u;
-          if (s0 + q < p.Ns) {
-            if (i < p.N)
-              h = p.sigma[(s0 + q) * p.N + i] < 0 ? 0xBF80u : 0x3F80u;
-            else if (i == p.N)
-              h = 0x3F80u;
+        for (int q = 0; q < 8; ++q)
+          v[q] = (4 * lane < p.N && s0 + q < p.Ns) ? *reinterpret_cast<const uint32_t *>(p.sigma + (s0 + q) * p.N + 4 * lane) : 0u;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int i = 4 * lane + r;
+          uint32_t pk[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            uint32_t h = 0u;
+            if (s0 + q < p.Ns) {
+              if (i < p.N)
+                h = ((v[q] >> (8 * r + 7)) & 1u) ? 0xBF80u : 0x3F80u;
+              else if (i == p.N)
+                h = 0x3F80u;
+            }
+            pk[q >> 1] |= h << (16 * (q & 1));
           }
-          pk[q >> 1] |= h << (16 * (q & 1));
+          *reinterpret_cast<uint4 *>(a_tile + (uint32_t)(i >> 3) * FT_SBO + (uint32_t)(i & 7) * 16u + (uint32_t)g * 128u) =
+              make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
-        *reinterpret_cast<uint4 *>(a_tile + (uint32_t)(i >> 3) * FT_SBO + (uint32_t)(i & 7) * 16u + (uint32_t)g * 128u) =
-            make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      } else {
+        for (int i = lane; i < 128; i += 32) {
+          uint32_t pk[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            uint32_t h = 0u;
+            if (s0 + q < p.Ns) {
+              if (i < p.N)
+                h = p.sigma[(s0 + q) * p.N + i] < 0 ? 0xBF80u : 0x3F80u;
+              else if (i == p.N)
+                h = 0x3F80u;
+            }
+            pk[q >> 1] |= h << (16 * (q & 1));
+          }
+          *reinterpret_cast<uint4 *>(a_tile + (uint32_t)(i >> 3) * FT_SBO + (uint32_t)(i & 7) * 16u + (uint32_t)g * 128u) =
+              make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
       }
       // ---- B'[j, s] = tanh(theta[s, j0 + j]) * w[s] in three bf16 parts; column NT = w (tile 0 only: F_a)
-      for (int j = lane; j < p.NTX; j += 32) {
-        const bool in_tile = j < p.NT && j0 + j < p.M;
-        float th[8];
+      // (FT_JB row iterations at a time: their 8 FT_JB loads are all in flight before the arithmetic starts - with one load batch
+      // per iteration the warp sat on the latency of HBM seven times per group: 25 % of the kernel's stall samples)
+      for (int jb = lane; jb < p.NTX; jb += 32 * FT_JB) {
+        float th[FT_JB][8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) th[q] = (in_tile && s0 + q < p.Ns) ? p.theta[(s0 + q) * p.M + j0 + j] : 0.0f;
-        uint32_t p1[4] = {0u, 0u, 0u, 0u}, p2[4] = {0u, 0u, 0u, 0u}, p3[4] = {0u, 0u, 0u, 0u};
+        for (int u = 0; u < FT_JB; ++u) {
+          const int j = jb + 32 * u;
+          const bool in_tile = j < p.NT && j0 + j < p.M;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float x = 0.0f;
-          if (in_tile)
-            x = (p.is_tanh ? th[q] : tanhf(th[q])) * w[q];
-          else if (j == p.NT && tile == 0)
-            x = w[q];
-          const uint32_t h1 = f32_to_bf16_rn(x);
-          const float r1 = x - bf16_to_f32((uint16_t)h1);
-          const uint32_t h2 = f32_to_bf16_rn(r1);
-          const float r2 = r1 - bf16_to_f32((uint16_t)h2);
-          const uint32_t h3 = f32_to_bf16_rn(r2);
-          p1[q >> 1] |= h1 << (16 * (q & 1));
-          p2[q >> 1] |= h2 << (16 * (q & 1));
-          p3[q >> 1] |= h3 << (16 * (q & 1));
+          for (int q = 0; q < 8; ++q) th[u][q] = (in_tile && s0 + q < p.Ns) ? p.theta[(s0 + q) * p.M + j0 + j] : 0.0f;
         }
-        unsigned char *dst = b_tiles + (uint32_t)(j >> 3) * FT_SBO + (uint32_t)(j & 7) * 16u + (uint32_t)g * 128u;
-        *reinterpret_cast<uint4 *>(dst) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
-        *reinterpret_cast<uint4 *>(dst + b_part_bytes) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
-        *reinterpret_cast<uint4 *>(dst + 2 * (size_t)b_part_bytes) = make_uint4(p3[0], p3[1], p3[2], p3[3]);
+#pragma unroll
+        for (int u = 0; u < FT_JB; ++u) {
+          const int j = jb + 32 * u;
+          if (j >= p.NTX) break;
+          const bool in_tile = j < p.NT && j0 + j < p.M;
+          uint32_t p1[4] = {0u, 0u, 0u, 0u}, p2[4] = {0u, 0u, 0u, 0u}, p3[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float x = 0.0f;
+            if (in_tile)
+              x = (p.is_tanh ? th[u][q] : tanhf(th[u][q])) * w[q];
+            else if (j == p.NT && tile == 0)
+              x = w[q];
+            const uint32_t h1 = f32_to_bf16_rn(x);
+            const float r1 = x - bf16_to_f32((uint16_t)h1);
+            const uint32_t h2 = f32_to_bf16_rn(r1);
+            const float r2 = r1 - bf16_to_f32((uint16_t)h2);
+            const uint32_t h3 = f32_to_bf16_rn(r2);
+            p1[q >> 1] |= h1 << (16 * (q & 1));
+            p2[q >> 1] |= h2 << (16 * (q & 1));
+            p3[q >> 1] |= h3 << (16 * (q & 1));
+          }
+          unsigned char *dst = b_tiles + (uint32_t)(j >> 3) * FT_SBO + (uint32_t)(j & 7) * 16u + (uint32_t)g * 128u;
+          *reinterpret_cast<uint4 *>(dst) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+          *reinterpret_cast<uint4 *>(dst + b_part_bytes) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+          *reinterpret_cast<uint4 *>(dst + 2 * (size_t)b_part_bytes) = make_uint4(p3[0], p3[1], p3[2], p3[3]);
+        }
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
