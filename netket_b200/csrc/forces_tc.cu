@@ -153,22 +153,26 @@ __global__ void __launch_bounds__(FT_THREADS, 1) forces_tc_kernel(const __grid_c
           const int j = jb + 32 * u;
           if (j >= p.NTX) break;
           const bool in_tile = j < p.NT && j0 + j < p.M;
-          uint32_t p1[4] = {0u, 0u, 0u, 0u}, p2[4] = {0u, 0u, 0u, 0u}, p3[4] = {0u, 0u, 0u, 0u};
+          // exact three-way bf16 split of two values at a time: cvt.rn.bf16x2.f32 packs a pair (element q in the low half,
+          // q + 1 in the high half: the K-major order of the tile), the residuals are exact fp32 subtractions
+          uint32_t p1[4], p2[4], p3[4];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float x = 0.0f;
-            if (in_tile)
-              x = (p.is_tanh ? th[u][q] : tanhf(th[u][q])) * w[q];
-            else if (j == p.NT && tile == 0)
-              x = w[q];
-            const uint32_t h1 = f32_to_bf16_rn(x);
-            const float r1 = x - bf16_to_f32((uint16_t)h1);
-            const uint32_t h2 = f32_to_bf16_rn(r1);
-            const float r2 = r1 - bf16_to_f32((uint16_t)h2);
-            const uint32_t h3 = f32_to_bf16_rn(r2);
-            p1[q >> 1] |= h1 << (16 * (q & 1));
-            p2[q >> 1] |= h2 << (16 * (q & 1));
-            p3[q >> 1] |= h3 << (16 * (q & 1));
+          for (int q = 0; q < 8; q += 2) {
+            float x0 = 0.0f, x1 = 0.0f;
+            if (in_tile) {
+              x0 = (p.is_tanh ? th[u][q] : tanhf(th[u][q])) * w[q];
+              x1 = (p.is_tanh ? th[u][q + 1] : tanhf(th[u][q + 1])) * w[q + 1];
+            } else if (j == p.NT && tile == 0) {
+              x0 = w[q];
+              x1 = w[q + 1];
+            }
+            const uint32_t h1 = pack_bf16x2_rn(x0, x1);
+            const float r0 = x0 - __uint_as_float(h1 << 16), r1 = x1 - __uint_as_float(h1 & 0xffff0000u);
+            const uint32_t h2 = pack_bf16x2_rn(r0, r1);
+            const float s0r = r0 - __uint_as_float(h2 << 16), s1r = r1 - __uint_as_float(h2 & 0xffff0000u);
+            p1[q >> 1] = h1;
+            p2[q >> 1] = h2;
+            p3[q >> 1] = pack_bf16x2_rn(s0r, s1r);
           }
           unsigned char *dst = b_tiles + (uint32_t)(j >> 3) * FT_SBO + (uint32_t)(j & 7) * 16u + (uint32_t)g * 128u;
           *reinterpret_cast<uint4 *>(dst) = make_uint4(p1[0], p1[1], p1[2], p1[3]);

@@ -24,6 +24,12 @@ __device__ __forceinline__ uint16_t f32_to_bf16_rn(float x) {
   return (uint16_t)(u >> 16);
 }
 __device__ __forceinline__ float bf16_to_f32(uint16_t h) { return __uint_as_float((uint32_t)h << 16); }
+// {bf16(lo) in bits 0..15, bf16(hi) in bits 16..31}, round to nearest even: one instruction for two conversions
+__device__ __forceinline__ uint32_t pack_bf16x2_rn(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
