@@ -90,7 +90,13 @@ struct TcArgs {
   uint32_t part_bytes, img_bytes;
 };
 
-__global__ void __launch_bounds__(128, 1) theta_tc_kernel(const __grid_constant__ TcArgs p) {
+#ifndef NK_TC_THREADS
+#define NK_TC_THREADS 512
+#endif
+constexpr int TC_THREADS = NK_TC_THREADS;  // TC_PARTS warps per TMEM lane quarter: they split the A-tile chunks and the accumulator's columns
+constexpr int TC_PARTS = TC_THREADS / 128;
+
+__global__ void __launch_bounds__(TC_THREADS, 1) theta_tc_kernel(const __grid_constant__ TcArgs p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char *b_img = smem;                          // 3 parts, K-major core-matrix layout
   unsigned char *a_tiles = smem + p.img_bytes;          // 2 x (128 x kpad bf16), same layout
@@ -99,6 +105,8 @@ __global__ void __launch_bounds__(128, 1) theta_tc_kernel(const __grid_constant_
   uint64_t *bar_load = bars, *bar_mma = bars + 1;       // bar_mma[0..1]
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3);
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int row_t = tid & 127;   // row of the 128-row block this thread works on (= TMEM lane: warp % 4 selects the lane quarter)
+  const int half_t = tid >> 7;   // which share of the K chunks (A tile) / of the columns (epilogue) it takes
   const int tile = blockIdx.x % p.nt;
   const int n0 = tile * p.NT;
 
@@ -133,14 +141,14 @@ __global__ void __launch_bounds__(128, 1) theta_tc_kernel(const __grid_constant_
                    : "memory");
     } while (!done);
   };
-  // A tile of row block rb into buffer `buf`: row = tid, sigma int8 -> bf16 (+1 = 0x3F80, -1 = 0xBF80), zero beyond N / B
+  // A tile of row block rb into buffer `buf`: row = tid % 128 (the two thread halves alternate over the 16-byte K chunks), sigma int8 -> bf16 (+1 = 0x3F80, -1 = 0xBF80), zero beyond N / B
   auto build_a = [&](int64_t rb, int buf) {
-    const int64_t row = rb * 128 + tid;
+    const int64_t row = rb * 128 + row_t;
     const int8_t *src = p.sigma + row * p.N;
-    unsigned char *dst = a_tiles + buf * a_bytes + (size_t)(tid >> 3) * p.sbo + (size_t)(tid & 7) * 16;
+    unsigned char *dst = a_tiles + buf * a_bytes + (size_t)(row_t >> 3) * p.sbo + (size_t)(row_t & 7) * 16;
     // rows of whole, aligned 32-bit words (row * N is then a multiple of 4): 4 spins per load
     const bool words = (p.N & 3) == 0 && (reinterpret_cast<uintptr_t>(p.sigma) & 3) == 0;
-    for (int c = 0; c < p.kpad / 8; ++c) {
+    for (int c = half_t; c < p.kpad / 8; c += TC_PARTS) {
       uint32_t w[4] = {0u, 0u, 0u, 0u};
       if (row < p.B) {
         if (words) {
@@ -218,10 +226,10 @@ __global__ void __launch_bounds__(128, 1) theta_tc_kernel(const __grid_constant_
     wait_bar(bar_mma + buf, (uint32_t)((it >> 1) & 1));
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     {
-      const int64_t row = rb * 128 + tid;
+      const int64_t row = rb * 128 + row_t;
       float *out = p.theta + row * p.M;
-      const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * p.acc_cols);
-      for (int c0 = 0; c0 < p.NT; c0 += 32) {
+      const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(buf * p.acc_cols);
+      for (int c0 = 32 * half_t; c0 < p.NT; c0 += 32 * TC_PARTS) {
         uint32_t r[32];
         const int width = min(32, p.NT - c0);
         if (width == 32)
@@ -330,7 +338,7 @@ int theta_gemm(cudaStream_t stream, const nk_rbm_t &rbm, const int8_t *sigma, in
   const int64_t n_blocks = (B + 127) / 128;
   int64_t ctas = (int64_t)(num_sms() / g.nt) * g.nt;
   if (ctas > n_blocks * g.nt) ctas = n_blocks * g.nt;
-  theta_tc_kernel<<<(int)ctas, 128, g.smem_bytes, stream>>>(a);
+  theta_tc_kernel<<<(int)ctas, TC_THREADS, g.smem_bytes, stream>>>(a);
   NK_LAUNCH_OK();
   return NK_OK;
 }
