@@ -97,6 +97,10 @@ __global__ void __launch_bounds__(256) prod_prep_tables(const __grid_constant__ 
     uint16_t *cl = reinterpret_cast<uint16_t *>(aux + L.cl_off);
     uint32_t *adj = reinterpret_cast<uint32_t *>(aux + L.adj_off);
     int *lg = reinterpret_cast<int *>(aux + L.lg_off);
+    if (s.cluster_probs != nullptr) {
+      double *cp = reinterpret_cast<double *>(aux + L.cp_off);
+      for (int c = tid; c < C; c += nt) cp[c] = s.cluster_probs[c];
+    }
     for (int c = tid; c < C; c += nt) {
       const int i = s.clusters[2 * c], j = s.clusters[2 * c + 1];
       if (i < 0 || j < 0 || i >= N || j >= N || i == j) {
@@ -292,6 +296,8 @@ static bool prod_layout(const SweepKernelArgs &a, const ProdShape &ps, ProdLayou
     off = align16(off + N);
     L->adj_off = off;
     off = align16(off + N * PROD_ADJ_MAX * 4);
+    L->cp_off = off;
+    if (a.cluster_probs != nullptr) off = align16(off + 8 * C);
   }
   if (a.eloc_kind == 1) {
     L->edges_off = off;

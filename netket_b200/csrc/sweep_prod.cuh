@@ -47,6 +47,7 @@ struct ProdLayout {
   int lg_off;                      // exchange: fix(log2(n) / machine_pow), n = 0..C
   int cl_off;                      // exchange: clusters as uint16 pairs
   int adjdeg_off, adj_off;         // exchange: clusters per site: degree (uint8), entries (cluster | partner << 16)
+  int cp_off;                      // exchange with probabilities=: the clusters' weights (double), staged with the other tables
   int edges_off;                   // Ising: edges as uint16 pairs
   int lop_sites_off[2], lop_diag_off[2], lop_mel_off[2], lop_code_off[2];  // LocalOperator, compact tables
   int hop_off, bar_off, smem_bytes;
@@ -434,7 +435,8 @@ __global__ void __launch_bounds__(prod::ProdWarps<T, RULE>::value * 32, 1) sweep
   const Rc *rctab = reinterpret_cast<const Rc *>(aux + L.rc_off);
   const int *lgtab = reinterpret_cast<const int *>(aux + L.lg_off);
   const uint16_t *cl = reinterpret_cast<const uint16_t *>(aux + L.cl_off);
-  const double *cprob = RULE == NK_RULE_EXCHANGE ? s.cluster_probs : nullptr;  // ExchangeRule(probabilities=) weights, or NULL
+  // ExchangeRule(probabilities=) weights (shared-memory copy: the selection walks them bit by bit), or NULL
+  const double *cprob = RULE == NK_RULE_EXCHANGE && s.cluster_probs != nullptr ? reinterpret_cast<const double *>(aux + L.cp_off) : nullptr;
   const uint8_t *adjdeg = aux + L.adjdeg_off;
   const uint32_t *adj = reinterpret_cast<const uint32_t *>(aux + L.adj_off);
   const uint16_t *edges = reinterpret_cast<const uint16_t *>(aux + L.edges_off);
