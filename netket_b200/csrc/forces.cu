@@ -130,7 +130,7 @@ __device__ __forceinline__ void dmma884_acc(double &d0, double &d1, double a, do
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(F_THREADS) forces_dmma_kernel(const __grid_constant__ ForcesArgs p) {
+__global__ void __launch_bounds__(F_THREADS, 2) forces_dmma_kernel(const __grid_constant__ ForcesArgs p) {
   __shared__ __align__(16) int8_t sg[FD_TS][F_TI + 4];   // sigma; row stride 132 bytes = 33 words (odd: conflict-free A fragments)
   __shared__ __align__(16) double xs[FD_TS][FD_XS];      // tanh(theta) * w
   __shared__ double ws[FD_TS];
@@ -144,6 +144,10 @@ __global__ void __launch_bounds__(F_THREADS) forces_dmma_kernel(const __grid_con
 #pragma unroll
     for (int b = 0; b < 8; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
   double fb = 0.0, fa = 0.0;
+  double fa4[4] = {0.0, 0.0, 0.0, 0.0};  // word path of the sigma tile: this thread's four sites
+  // sigma rows of whole, aligned 32-bit words: 8 word loads per thread and batch, all in flight together (the byte path issues 32
+  // loads in groups of 4: with ~16 warps per SM the staging sat on the latency of HBM eight times per batch)
+  const bool sig_words = (p.N & 3) == 0 && (i0 & 3) == 0 && (reinterpret_cast<uintptr_t>(p.sigma) & 3) == 0;
   const int64_t n_batches = (p.Ns + FD_TS - 1) / FD_TS;
   for (int64_t bt = blockIdx.x; bt < n_batches; bt += gridDim.x) {
     const int64_t s0 = bt * FD_TS;
@@ -155,7 +159,23 @@ __global__ void __launch_bounds__(F_THREADS) forces_dmma_kernel(const __grid_con
       ws[t] = w;
     }
     __syncthreads();
-    {  // sigma tile: thread t -> site i0 + (t & 127), samples (t >> 7) + 2 k
+    if (sig_words) {  // sigma tile: thread t -> sites i0 + 4 (t & 31) .. + 3, samples (t >> 5) + 8 k
+      const int wc = t & 31;
+      uint32_t v[FD_TS / 8];
+#pragma unroll
+      for (int k = 0; k < FD_TS / 8; ++k) {
+        const int64_t s = s0 + (t >> 5) + 8 * k;
+        v[k] = (i0 + 4 * wc < p.N && s < p.Ns) ? *reinterpret_cast<const uint32_t *>(p.sigma + s * p.N + i0 + 4 * wc) : 0u;
+      }
+#pragma unroll
+      for (int k = 0; k < FD_TS / 8; ++k) {
+        const int sl = (t >> 5) + 8 * k;
+        *reinterpret_cast<uint32_t *>(&sg[sl][4 * wc]) = v[k];
+        const double w = ws[sl];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) fa4[r] += (double)(int8_t)(v[k] >> (8 * r)) * w;
+      }
+    } else {  // sigma tile: thread t -> site i0 + (t & 127), samples (t >> 7) + 2 k
       const int i = i0 + (t & 127);
 #pragma unroll 4
       for (int k = 0; k < FD_TS / 2; ++k) {
@@ -167,16 +187,23 @@ __global__ void __launch_bounds__(F_THREADS) forces_dmma_kernel(const __grid_con
         fa += (double)v * ws[sl];
       }
     }
-    {  // x tile: thread t -> hidden unit j0 + (t & 63), samples (t >> 6) + 4 k
+    {  // x tile: thread t -> hidden unit j0 + (t & 63), samples (t >> 6) + 4 k; 8 loads in flight at a time
       const int j = j0 + (t & 63);
-#pragma unroll 4
-      for (int k = 0; k < FD_TS / 4; ++k) {
-        const int sl = (t >> 6) + 4 * k;
-        const int64_t s = s0 + sl;
-        double v = 0.0;
-        if (j < p.M && s < p.Ns) v = (p.is_tanh ? theta[s * p.M + j] : tanh(theta[s * p.M + j])) * ws[sl];
-        xs[sl][t & 63] = v;
-        fb += v;
+#pragma unroll
+      for (int kb = 0; kb < FD_TS / 4; kb += 8) {
+        double th[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int64_t s = s0 + (t >> 6) + 4 * (kb + k);
+          th[k] = (j < p.M && s < p.Ns) ? theta[s * p.M + j] : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int sl = (t >> 6) + 4 * (kb + k);
+          const double v = (p.is_tanh ? th[k] : tanh(th[k])) * ws[sl];
+          xs[sl][t & 63] = v;
+          fb += v;
+        }
       }
     }
     __syncthreads();
@@ -206,7 +233,15 @@ __global__ void __launch_bounds__(F_THREADS) forces_dmma_kernel(const __grid_con
     }
   }
   if (p.want_b && blockIdx.z == 0 && j0 + (t & 63) < p.M) atomicAdd(p.sums + (size_t)p.N * p.M + j0 + (t & 63), fb);
-  if (p.want_a && blockIdx.y == 0 && i0 + (t & 127) < p.N) atomicAdd(p.sums + (size_t)p.N * p.M + p.M + i0 + (t & 127), fa);
+  if (p.want_a && blockIdx.y == 0) {
+    if (sig_words) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (i0 + 4 * (t & 31) + r < p.N) atomicAdd(p.sums + (size_t)p.N * p.M + p.M + i0 + 4 * (t & 31) + r, fa4[r]);
+    } else if (i0 + (t & 127) < p.N) {
+      atomicAdd(p.sums + (size_t)p.N * p.M + p.M + i0 + (t & 127), fa);
+    }
+  }
 }
 
 template <typename T>

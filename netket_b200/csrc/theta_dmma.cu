@@ -29,13 +29,30 @@ __global__ void __launch_bounds__(256) theta_dmma_kernel(const int8_t *__restric
     Ws[k * DM_WSTRIDE + c] = (k < N && j0 + c < M) ? W[(size_t)k * M + j0 + c] : 0.0;
   }
   const int fr = lane >> 2, fc = lane & 3;  // fragment row / column of this thread
+  const bool sig_words = (N & 3) == 0 && N <= 128 && (sstride & 3) == 0 && (reinterpret_cast<uintptr_t>(sigma) & 3) == 0;
   const int64_t n_blocks = (B + DM_ROWS - 1) / DM_ROWS;
   for (int64_t rb = blockIdx.x; rb < n_blocks; rb += gridDim.x) {
     __syncthreads();  // W tile ready / previous block's sigma consumed
     const int64_t row0 = rb * DM_ROWS;
-    for (int e = t; e < DM_ROWS * kpad; e += 256) {
-      const int r = e / kpad, k = e - r * kpad;
-      sg[r * sstride + k] = (k < N && row0 + r < B) ? sigma[(row0 + r) * N + k] : (int8_t)0;
+    if (sig_words) {
+      // rows of whole, aligned 32-bit words (N = kpad <= 128): a warp loads one row per instruction, DM_ROWS / 8 independent loads per
+      // thread, all in flight together (the byte loop below issues ~50 dependent-address loads per thread and block)
+      const int cw = t & 31, nw = N >> 2;
+      uint32_t v[DM_ROWS / 8];
+#pragma unroll
+      for (int i = 0; i < DM_ROWS / 8; ++i) {
+        const int r = (t >> 5) + 8 * i;
+        v[i] = (cw < nw && row0 + r < B) ? *reinterpret_cast<const uint32_t *>(sigma + (row0 + r) * N + 4 * cw) : 0u;
+      }
+      if (cw < nw) {
+#pragma unroll
+        for (int i = 0; i < DM_ROWS / 8; ++i) *reinterpret_cast<uint32_t *>(sg + ((t >> 5) + 8 * i) * sstride + 4 * cw) = v[i];
+      }
+    } else {
+      for (int e = t; e < DM_ROWS * kpad; e += 256) {
+        const int r = e / kpad, k = e - r * kpad;
+        sg[r * sstride + k] = (k < N && row0 + r < B) ? sigma[(row0 + r) * N + k] : (int8_t)0;
+      }
     }
     __syncthreads();
     double acc[2][8][2];
